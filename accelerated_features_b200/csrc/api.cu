@@ -1,0 +1,155 @@
+// C-ABI glue: context, error reporting and the backbone schedule (XFeatModel.forward, model.py:123-154).
+#include <stdarg.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace xf {
+
+static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// Activation buffers of one forward pass (NHWC fp32), carved from the caller's workspace.
+struct NetWs {
+  float *a1, *a2, *a3, *x1s, *t4a, *x2;       // stem + block2 (1/1, 1/2, 1/4 res)
+  float *t8a, *t8b, *x3, *fin, *f1, *f2;      // 1/8 res, 64 ch
+  float *t16a, *t16b, *x4;                    // 1/16 res, 64 ch
+  float *t32a, *t32b, *x5;                    // 1/32 res, 128/128/64 ch
+};
+
+static void carve_net(Bump& bump, int B, int H, int W, NetWs& ws) {
+  const size_t p1 = (size_t)B * H * W, p2 = p1 / 4, p4 = p1 / 16, p8 = p1 / 64, p16 = p1 / 256, p32 = p1 / 1024;
+  ws.a1 = bump.take<float>(p1 * 4);
+  ws.a2 = bump.take<float>(p2 * 8);
+  ws.a3 = bump.take<float>(p2 * 8);
+  ws.x1s = bump.take<float>(p4 * 24);
+  ws.t4a = bump.take<float>(p4 * 24);
+  ws.x2 = bump.take<float>(p4 * 24);
+  ws.t8a = bump.take<float>(p8 * 64);
+  ws.t8b = bump.take<float>(p8 * 64);
+  ws.x3 = bump.take<float>(p8 * 64);
+  ws.fin = bump.take<float>(p8 * 64);
+  ws.f1 = bump.take<float>(p8 * 64);
+  ws.f2 = bump.take<float>(p8 * 64);
+  ws.t16a = bump.take<float>(p16 * 64);
+  ws.t16b = bump.take<float>(p16 * 64);
+  ws.x4 = bump.take<float>(p16 * 64);
+  ws.t32a = bump.take<float>(p32 * 128);
+  ws.t32b = bump.take<float>(p32 * 128);
+  ws.x5 = bump.take<float>(p32 * 64);
+}
+
+}  // namespace xf
+
+extern "C" int xfeat_abi_version(void) { return XFEAT_ABI_VERSION; }
+extern "C" const char* xfeat_last_error(void) { return xf::g_err; }
+extern "C" unsigned long long xfeat_launch_count(void) { return xf::g_launches; }
+extern "C" size_t xfeat_packed_weight_floats(void) { return xf::make_layer_table().total; }
+
+extern "C" int xfeat_create(xfeat_ctx** out, int device, const float* packed_host, size_t n_floats) {
+  XF_REQUIRE(out && packed_host, "create: null pointer");
+  const xf::LayerTable t = xf::make_layer_table();
+  XF_REQUIRE(n_floats == t.total, "create: packed blob has %zu floats, expected %zu", n_floats, t.total);
+  XF_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  XF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    xf::set_error("create: device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    return XF_E_UNSUPPORTED;
+  }
+  xfeat_ctx* c = new xfeat_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->table = t;
+  c->h_weights = (float*)malloc(sizeof(float) * t.total);
+  memcpy(c->h_weights, packed_host, sizeof(float) * t.total);
+  c->d_weights = nullptr;
+  cudaError_t e = cudaMalloc(&c->d_weights, sizeof(float) * t.total);
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_weights, packed_host, sizeof(float) * t.total, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    xf::set_error("create: weight upload failed: %s", cudaGetErrorString(e));
+    if (c->d_weights) cudaFree(c->d_weights);
+    free(c->h_weights);
+    delete c;
+    return XF_E_CUDA;
+  }
+  *out = c;
+  return XF_OK;
+}
+
+extern "C" void xfeat_destroy(xfeat_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_weights) cudaFree(ctx->d_weights);
+  free(ctx->h_weights);
+  delete ctx;
+}
+
+extern "C" size_t xfeat_net_workspace_bytes(int B, int H, int W) {
+  xf::Bump bump(nullptr, 0);
+  xf::NetWs ws;
+  xf::carve_net(bump, B, H, W, ws);
+  return bump.used();
+}
+
+extern "C" int xfeat_net(xfeat_ctx* ctx, const float* d_xn, int B, int H, int W, float* d_feats, float* d_heat,
+                         float* d_reliability, float* d_kpt_logits, void* d_ws, size_t ws_bytes, void* stream) {
+  using namespace xf;
+  XF_REQUIRE(ctx && d_xn && d_feats && d_heat && d_reliability && d_ws, "net: null pointer");
+  XF_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, "net: bad shape B=%d H=%d W=%d", B, H, W);
+  XF_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  Bump bump(d_ws, ws_bytes);
+  NetWs ws;
+  carve_net(bump, B, H, W, ws);
+  if (!bump.ok) {
+    set_error("net: workspace too small (%zu < %zu)", ws_bytes, bump.used());
+    return XF_E_WORKSPACE;
+  }
+  const int H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16, H32 = H / 32, W32 = W / 32;
+  int rc;
+#define XF_RUN(call) \
+  if ((rc = (call)) != XF_OK) return rc
+  // block1 + skip1 -> x1 + skip1(x)                                              model.py:139-140
+  XF_RUN(launch_stem_chain(ctx->h_weights, ctx->table, d_xn, ws.a1, ws.a2, ws.a3, ws.x1s, B, H, W, st));
+  // block2                                                                       model.py:140
+  XF_RUN(launch_conv_layer(ctx, L_B2_0, ws.x1s, IN_NHWC, B, H4, W4, ws.t4a, st));
+  XF_RUN(launch_conv_layer(ctx, L_B2_1, ws.t4a, IN_NHWC, B, H4, W4, ws.x2, st));
+  // block3                                                                       model.py:141
+  XF_RUN(launch_conv_layer(ctx, L_B3_0, ws.x2, IN_NHWC, B, H4, W4, ws.t8a, st));
+  XF_RUN(launch_conv_layer(ctx, L_B3_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
+  XF_RUN(launch_conv_layer(ctx, L_B3_2, ws.t8b, IN_NHWC, B, H8, W8, ws.x3, st));
+  // block4                                                                       model.py:142
+  XF_RUN(launch_conv_layer(ctx, L_B4_0, ws.x3, IN_NHWC, B, H8, W8, ws.t16a, st));
+  XF_RUN(launch_conv_layer(ctx, L_B4_1, ws.t16a, IN_NHWC, B, H16, W16, ws.t16b, st));
+  XF_RUN(launch_conv_layer(ctx, L_B4_2, ws.t16b, IN_NHWC, B, H16, W16, ws.x4, st));
+  // block5                                                                       model.py:143
+  XF_RUN(launch_conv_layer(ctx, L_B5_0, ws.x4, IN_NHWC, B, H16, W16, ws.t32a, st));
+  XF_RUN(launch_conv_layer(ctx, L_B5_1, ws.t32a, IN_NHWC, B, H32, W32, ws.t32b, st));
+  XF_RUN(launch_conv_layer(ctx, L_B5_2, ws.t32b, IN_NHWC, B, H32, W32, ws.t32a, st));
+  XF_RUN(launch_conv_layer(ctx, L_B5_3, ws.t32a, IN_NHWC, B, H32, W32, ws.x5, st));
+  // pyramid fusion                                                               model.py:146-148
+  XF_RUN(launch_fuse_pyramid(ws.x3, ws.x4, ws.x5, ws.fin, B, H8, W8, st));
+  XF_RUN(launch_conv_layer(ctx, L_FU_0, ws.fin, IN_NHWC, B, H8, W8, ws.f1, st));
+  XF_RUN(launch_conv_layer(ctx, L_FU_1, ws.f1, IN_NHWC, B, H8, W8, ws.f2, st));
+  XF_RUN(launch_conv_layer(ctx, L_FU_2, ws.f2, IN_NHWC, B, H8, W8, d_feats, st));
+  // reliability head                                                             model.py:151
+  XF_RUN(launch_conv_layer(ctx, L_HH_0, d_feats, IN_NHWC, B, H8, W8, ws.t8a, st));
+  XF_RUN(launch_conv_layer(ctx, L_HH_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
+  XF_RUN(launch_reliability(ctx, ws.t8b, d_reliability, (int64_t)B * H8 * W8, st));
+  // keypoint head on the 8x8-unfolded gray image, softmax + depth-to-space        model.py:152, xfeat.py:242-247
+  XF_RUN(launch_conv_layer(ctx, L_KH_0, d_xn, IN_UNFOLD8, B, H8, W8, ws.t8a, st));
+  XF_RUN(launch_conv_layer(ctx, L_KH_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
+  XF_RUN(launch_conv_layer(ctx, L_KH_2, ws.t8b, IN_NHWC, B, H8, W8, ws.t8a, st));
+  XF_RUN(launch_kpt_softmax(ctx, ws.t8a, d_heat, d_kpt_logits, B, H8, W8, st));
+#undef XF_RUN
+  return XF_OK;
+}

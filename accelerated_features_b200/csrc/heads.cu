@@ -1,0 +1,148 @@
+// Small fused kernels around the conv stack: pyramid fusion input (model.py:146-148), reliability head tail
+// (heatmap_head.2 + sigmoid, model.py:82-83), keypoint head tail (keypoint_head.3 + softmax(65) + drop dustbin +
+// 8x8 depth-to-space, model.py:91 + xfeat.py:242-247).
+#include "common.cuh"
+
+namespace xf {
+
+// out = x3 + up2(x4) + up4(x5)   (NHWC, 64 channels; bilinear, align_corners=False; F.interpolate to x3's size)
+__global__ void __launch_bounds__(256) fuse_pyramid_kernel(const float* __restrict__ x3, const float* __restrict__ x4,
+                                                           const float* __restrict__ x5, float* __restrict__ out,
+                                                           int H3, int W3, int H4, int W4, int H5, int W5,
+                                                           int64_t total4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = (int)(i & 15);
+  int64_t p = i >> 4;
+  const int x = (int)(p % W3);
+  p /= W3;
+  const int y = (int)(p % H3);
+  const int b = (int)(p / H3);
+  float4 r = __ldg(reinterpret_cast<const float4*>(x3) + i);
+  {
+    const LinTap ty = lin_tap(y, (float)H4 / (float)H3, H4), tx = lin_tap(x, (float)W4 / (float)W3, W4);
+    const float4* base = reinterpret_cast<const float4*>(x4) + (int64_t)b * H4 * W4 * 16 + c4;
+    const float4 v00 = __ldg(base + ((int64_t)ty.i0 * W4 + tx.i0) * 16), v01 = __ldg(base + ((int64_t)ty.i0 * W4 + tx.i1) * 16);
+    const float4 v10 = __ldg(base + ((int64_t)ty.i1 * W4 + tx.i0) * 16), v11 = __ldg(base + ((int64_t)ty.i1 * W4 + tx.i1) * 16);
+#define XF_BIL(f) (ty.l0 * (tx.l0 * v00.f + tx.l1 * v01.f) + ty.l1 * (tx.l0 * v10.f + tx.l1 * v11.f))
+    r.x += XF_BIL(x); r.y += XF_BIL(y); r.z += XF_BIL(z); r.w += XF_BIL(w);
+  }
+  {
+    const LinTap ty = lin_tap(y, (float)H5 / (float)H3, H5), tx = lin_tap(x, (float)W5 / (float)W3, W5);
+    const float4* base = reinterpret_cast<const float4*>(x5) + (int64_t)b * H5 * W5 * 16 + c4;
+    const float4 v00 = __ldg(base + ((int64_t)ty.i0 * W5 + tx.i0) * 16), v01 = __ldg(base + ((int64_t)ty.i0 * W5 + tx.i1) * 16);
+    const float4 v10 = __ldg(base + ((int64_t)ty.i1 * W5 + tx.i0) * 16), v11 = __ldg(base + ((int64_t)ty.i1 * W5 + tx.i1) * 16);
+    r.x += XF_BIL(x); r.y += XF_BIL(y); r.z += XF_BIL(z); r.w += XF_BIL(w);
+#undef XF_BIL
+  }
+  reinterpret_cast<float4*>(out)[i] = r;
+}
+
+// reliability = sigmoid(t . w + b), t: (npix,64) NHWC. 8 lanes per pixel, 8 channels per lane.
+__global__ void __launch_bounds__(256) reliability_kernel(const float* __restrict__ t, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ out,
+                                                          int64_t npix) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t pix = gid >> 3;
+  const int sub = (int)(gid & 7);
+  float s = 0.f;
+  if (pix < npix) {
+    const float4* tp = reinterpret_cast<const float4*>(t + pix * 64) + sub * 2;
+    const float4* wp = reinterpret_cast<const float4*>(w) + sub * 2;
+    const float4 a0 = __ldg(tp), a1 = __ldg(tp + 1), w0 = __ldg(wp), w1 = __ldg(wp + 1);
+    s = a0.x * w0.x + a0.y * w0.y + a0.z * w0.z + a0.w * w0.w + a1.x * w1.x + a1.y * w1.y + a1.z * w1.z + a1.w * w1.w;
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (pix < npix && sub == 0) {
+    const float z = s + __ldg(bias);
+    out[pix] = 1.0f / (1.0f + expf(-z));
+  }
+}
+
+// keypoint_head.3 (64->65, bias) + softmax over the 65 logits + heat[b, 8h+i, 8w+j] = p[8i+j].
+// One warp per cell, CELLS cells per warp pass; weights [64][65] live in shared memory (stride 65: conflict-free
+// when lanes walk the output-channel axis), the cell's 64 inputs are staged per warp and broadcast.
+constexpr int KPT_WARPS = 8;
+__global__ void __launch_bounds__(KPT_WARPS * 32) kpt_softmax_kernel(const float* __restrict__ t,
+                                                                     const float* __restrict__ w,
+                                                                     const float* __restrict__ bias,
+                                                                     float* __restrict__ heat,
+                                                                     float* __restrict__ logits_out, int Hc, int Wc,
+                                                                     int64_t ncell) {
+  __shared__ float sW[64 * 65];
+  __shared__ float sB[65];
+  __shared__ float sT[KPT_WARPS][64];
+  for (int i = threadIdx.x; i < 64 * 65; i += blockDim.x) sW[i] = __ldg(w + i);
+  if (threadIdx.x < 65) sB[threadIdx.x] = __ldg(bias + threadIdx.x);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int W = Wc * 8;
+  for (int64_t cell = (int64_t)blockIdx.x * KPT_WARPS + warp; cell < ncell; cell += (int64_t)gridDim.x * KPT_WARPS) {
+    const float2 tv = __ldg(reinterpret_cast<const float2*>(t + cell * 64) + lane);
+    __syncwarp();
+    sT[warp][2 * lane] = tv.x;
+    sT[warp][2 * lane + 1] = tv.y;
+    __syncwarp();
+    float l0 = sB[lane], l1 = sB[lane + 32], l2 = sB[64];
+#pragma unroll 16
+    for (int k = 0; k < 64; ++k) {
+      const float a = sT[warp][k];
+      l0 = fmaf(a, sW[k * 65 + lane], l0);
+      l1 = fmaf(a, sW[k * 65 + lane + 32], l1);
+      l2 = fmaf(a, sW[k * 65 + 64], l2);
+    }
+    if (logits_out) {
+      float* lo = logits_out + cell * 65;
+      lo[lane] = l0;
+      lo[lane + 32] = l1;
+      if (lane == 0) lo[64] = l2;
+    }
+    float m = fmaxf(fmaxf(l0, l1), l2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+    float s = e0 + e1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s += e2;
+    const int64_t b = cell / ((int64_t)Hc * Wc);
+    const int rem = (int)(cell - b * Hc * Wc);
+    const int h = rem / Wc, wc = rem - h * Wc;
+    // channel c = 8i + j -> pixel (8h+i, 8wc+j): lane -> (i = lane>>3, j = lane&7), second half i += 4
+    float* hp = heat + ((int64_t)b * Hc * 8 + h * 8 + (lane >> 3)) * W + wc * 8 + (lane & 7);
+    hp[0] = e0 / s;
+    hp[(int64_t)4 * W] = e1 / s;
+  }
+}
+
+int launch_fuse_pyramid(const float* x3, const float* x4, const float* x5, float* out, int B, int H3, int W3,
+                        cudaStream_t st) {
+  const int64_t total4 = (int64_t)B * H3 * W3 * 16;
+  fuse_pyramid_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(x3, x4, x5, out, H3, W3, H3 / 2, W3 / 2, H3 / 4,
+                                                                         W3 / 4, total4);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+int launch_reliability(const xfeat_ctx* ctx, const float* t, float* out, int64_t npix, cudaStream_t st) {
+  const float* w = ctx->d_weights + ctx->table.w_off[L_HH_2];
+  const float* b = ctx->d_weights + ctx->table.b_off[L_HH_2];
+  reliability_kernel<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, st>>>(t, w, b, out, npix);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+int launch_kpt_softmax(const xfeat_ctx* ctx, const float* t, float* heat, float* logits, int B, int Hc, int Wc,
+                       cudaStream_t st) {
+  const float* w = ctx->d_weights + ctx->table.w_off[L_KH_3];
+  const float* b = ctx->d_weights + ctx->table.b_off[L_KH_3];
+  const int64_t ncell = (int64_t)B * Hc * Wc;
+  const int blocks = (int)std::min<int64_t>((ncell + KPT_WARPS - 1) / KPT_WARPS, (int64_t)ctx->sm_count * 8);
+  kpt_softmax_kernel<<<blocks, KPT_WARPS * 32, 0, st>>>(t, w, b, heat, logits, Hc, Wc, ncell);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+}  // namespace xf

@@ -1,0 +1,154 @@
+// Image ingest: bilinear resize, channel mean, per-image instance normalisation.
+// Reference: preprocess_tensor (xfeat.py:219-240), XFeatModel.forward normalisation (model.py:135-136),
+// extract_dualscale's F.interpolate (xfeat.py:380-381).  All HBM-bound streaming kernels.
+#include "common.cuh"
+
+namespace xf {
+
+template <int DTYPE>
+__device__ __forceinline__ float load_px(const void* p, int64_t off, int div255) {
+  float v;
+  if (DTYPE == XF_DTYPE_U8) v = (float)((const unsigned char*)p)[off];
+  else v = __ldg((const float*)p + off);
+  if (div255) v = __fdiv_rn(v, 255.0f);
+  return v;
+}
+
+// One thread per output pixel: bilinear sample of every channel (ATen upsample_bilinear2d arithmetic), mean over
+// channels, write gray; block-reduce sum / sum-of-squares in double -> atomicAdd into stats[b] = {sum, sumsq}.
+template <int DTYPE>
+__global__ void __launch_bounds__(256) gray_resize_kernel(const void* __restrict__ img, int C, int Hi, int Wi,
+                                                          int64_t sb, int64_t sc, int64_t sh, int64_t sw, int div255,
+                                                          int H, int W, float scale_h, float scale_w,
+                                                          float* __restrict__ gray, double* __restrict__ stats) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  float g = 0.f;
+  const bool in = (x < W) && (y < H);
+  if (in) {
+    const LinTap ty = lin_tap(y, scale_h, Hi);
+    const LinTap tx = lin_tap(x, scale_w, Wi);
+    const int64_t base = (int64_t)b * sb;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const int64_t bc = base + (int64_t)c * sc;
+      const float v00 = load_px<DTYPE>(img, bc + ty.i0 * sh + tx.i0 * sw, div255);
+      const float v01 = load_px<DTYPE>(img, bc + ty.i0 * sh + tx.i1 * sw, div255);
+      const float v10 = load_px<DTYPE>(img, bc + ty.i1 * sh + tx.i0 * sw, div255);
+      const float v11 = load_px<DTYPE>(img, bc + ty.i1 * sh + tx.i1 * sw, div255);
+      // ATen: l0h*(l0w*v00 + l1w*v01) + l1h*(l0w*v10 + l1w*v11)
+      const float top = __fadd_rn(__fmul_rn(tx.l0, v00), __fmul_rn(tx.l1, v01));
+      const float bot = __fadd_rn(__fmul_rn(tx.l0, v10), __fmul_rn(tx.l1, v11));
+      const float v = __fadd_rn(__fmul_rn(ty.l0, top), __fmul_rn(ty.l1, bot));
+      acc = __fadd_rn(acc, v);
+    }
+    g = (C == 1) ? acc : __fdiv_rn(acc, (float)C);
+    gray[((int64_t)b * H + y) * W + x] = g;
+  }
+  double s = in ? (double)g : 0.0, ss = in ? (double)g * (double)g : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  __shared__ double sh_s[8], sh_ss[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh_s[warp] = s; sh_ss[warp] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += sh_s[i]; c2 += sh_ss[i]; }
+    atomicAdd(&stats[2 * b], a);
+    atomicAdd(&stats[2 * b + 1], c2);
+  }
+}
+
+// InstanceNorm2d(1): (g - mean) * rsqrt(var_biased + 1e-5), float4 vectorised, in place.
+__global__ void __launch_bounds__(256) instnorm_kernel(float* __restrict__ gray, const double* __restrict__ stats,
+                                                       int HW4) {
+  const int b = blockIdx.y;
+  const double n = (double)HW4 * 4.0;
+  const double mean = stats[2 * b] / n;
+  double var = stats[2 * b + 1] / n - mean * mean;
+  if (var < 0) var = 0;
+  const float meanf = (float)mean;
+  const float invstd = (float)(1.0 / sqrt(var + 1e-5));
+  float4* p = reinterpret_cast<float4*>(gray) + (int64_t)b * HW4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW4; i += gridDim.x * blockDim.x) {
+    float4 v = p[i];
+    v.x = __fmul_rn(__fsub_rn(v.x, meanf), invstd);
+    v.y = __fmul_rn(__fsub_rn(v.y, meanf), invstd);
+    v.z = __fmul_rn(__fsub_rn(v.z, meanf), invstd);
+    v.w = __fmul_rn(__fsub_rn(v.w, meanf), invstd);
+    p[i] = v;
+  }
+}
+
+template <int DTYPE>
+__global__ void __launch_bounds__(256) resize_bilinear_kernel(const void* __restrict__ in, int C, int Hi, int Wi,
+                                                              int64_t sb, int64_t sc, int64_t sh, int64_t sw, int div255,
+                                                              float* __restrict__ out, int Ho, int Wo, float scale_h,
+                                                              float scale_w) {
+  const int plane = blockIdx.z;  // b*C + c
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= Wo || y >= Ho) return;
+  const LinTap ty = lin_tap(y, scale_h, Hi);
+  const LinTap tx = lin_tap(x, scale_w, Wi);
+  const int64_t base = (int64_t)(plane / C) * sb + (int64_t)(plane % C) * sc;
+  const float v00 = load_px<DTYPE>(in, base + ty.i0 * sh + tx.i0 * sw, div255);
+  const float v01 = load_px<DTYPE>(in, base + ty.i0 * sh + tx.i1 * sw, div255);
+  const float v10 = load_px<DTYPE>(in, base + ty.i1 * sh + tx.i0 * sw, div255);
+  const float v11 = load_px<DTYPE>(in, base + ty.i1 * sh + tx.i1 * sw, div255);
+  const float top = __fadd_rn(__fmul_rn(tx.l0, v00), __fmul_rn(tx.l1, v01));
+  const float bot = __fadd_rn(__fmul_rn(tx.l0, v10), __fmul_rn(tx.l1, v11));
+  out[((int64_t)plane * Ho + y) * Wo + x] = __fadd_rn(__fmul_rn(ty.l0, top), __fmul_rn(ty.l1, bot));
+}
+
+}  // namespace xf
+
+extern "C" int xfeat_resize_bilinear(const void* d_in, int dtype, int B, int C, int Hi, int Wi, int64_t stride_b,
+                                     int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255, float* d_out,
+                                     int Ho, int Wo, float scale_h, float scale_w, void* stream) {
+  XF_REQUIRE(d_in && d_out && B > 0 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "resize: bad arguments");
+  XF_REQUIRE((int64_t)B * C <= 65535, "resize: B*C too large for grid.z");
+  XF_REQUIRE(dtype == XF_DTYPE_F32 || dtype == XF_DTYPE_U8, "resize: unsupported dtype %d", dtype);
+  dim3 grid(xf::cdiv(Wo, 64), xf::cdiv(Ho, 4), B * C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == XF_DTYPE_F32)
+    xf::resize_bilinear_kernel<XF_DTYPE_F32><<<grid, 256, 0, st>>>(d_in, C, Hi, Wi, stride_b, stride_c, stride_h, stride_w,
+                                                                  div255, d_out, Ho, Wo, scale_h, scale_w);
+  else
+    xf::resize_bilinear_kernel<XF_DTYPE_U8><<<grid, 256, 0, st>>>(d_in, C, Hi, Wi, stride_b, stride_c, stride_h, stride_w,
+                                                                 div255, d_out, Ho, Wo, scale_h, scale_w);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+extern "C" int xfeat_preprocess(const void* d_img, int dtype, int B, int C, int Hi, int Wi, int64_t stride_b,
+                                int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255, int H, int W,
+                                float* d_xn, double* d_stats, void* stream) {
+  XF_REQUIRE(d_img && d_xn && d_stats, "preprocess: null pointer");
+  XF_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hi > 0 && Wi > 0, "preprocess: bad shape");
+  XF_REQUIRE(H > 0 && W > 0 && (H % 32) == 0 && (W % 32) == 0, "preprocess: H, W must be positive multiples of 32");
+  XF_REQUIRE(dtype == XF_DTYPE_F32 || dtype == XF_DTYPE_U8, "preprocess: unsupported dtype %d", dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  XF_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * 2 * B, st));
+  // ATen area_pixel_compute_scale (size given): scale = float(in) / out
+  const float sh = (float)Hi / (float)H, sw = (float)Wi / (float)W;
+  dim3 grid(xf::cdiv(W, 64), xf::cdiv(H, 4), B);
+  if (dtype == XF_DTYPE_F32)
+    xf::gray_resize_kernel<XF_DTYPE_F32><<<grid, 256, 0, st>>>(d_img, C, Hi, Wi, stride_b, stride_c, stride_h, stride_w,
+                                                              div255, H, W, sh, sw, d_xn, d_stats);
+  else
+    xf::gray_resize_kernel<XF_DTYPE_U8><<<grid, 256, 0, st>>>(d_img, C, Hi, Wi, stride_b, stride_c, stride_h, stride_w,
+                                                             div255, H, W, sh, sw, d_xn, d_stats);
+  XF_LAUNCH_CHECK();
+  const int HW4 = H * W / 4;
+  dim3 g2(std::min(xf::cdiv(HW4, 256), 1024), B);
+  xf::instnorm_kernel<<<g2, 256, 0, st>>>(d_xn, d_stats, HW4);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}

@@ -1,0 +1,259 @@
+// Sparse keypoint selection + description (xfeat.py:70-103):
+//   nms_score_kernel   : 5x5 max-pool equality NMS + threshold (XFeat.NMS, xfeat.py:249-263) fused with the score
+//                        nearest(K1h) * bilinear(H1) (xfeat.py:77-80) -> (score, pixel) keys appended per image;
+//   cub segmented sort : argsort(-scores) (xfeat.py:83) with a deterministic tie rule (score desc, raster index asc);
+//   sample_desc_kernel : top-k cut, bicubic sampling of the channel-normalised feature map (xfeat.py:70,90),
+//                        L2 normalisation (xfeat.py:93), keypoint rescale (xfeat.py:96), valid count (xfeat.py:98).
+// Everything stays on the device with fixed-capacity buffers; the only host-visible scalars are the per-image counts.
+#include <cub/device/device_segmented_sort.cuh>
+
+#include "common.cuh"
+
+namespace xf {
+
+constexpr int NMS_TX = 64, NMS_TY = 16, NMS_R = 2;
+
+__global__ void __launch_bounds__(256) nms_score_kernel(const float* __restrict__ heat, const float* __restrict__ rel,
+                                                        int H, int W, int Hm, int Wm, float thr, int cap,
+                                                        unsigned long long* __restrict__ keys,
+                                                        int* __restrict__ n_keep, int* __restrict__ n_cand) {
+  __shared__ float sIn[NMS_TY + 2 * NMS_R][NMS_TX + 2 * NMS_R];
+  __shared__ float sRow[NMS_TY + 2 * NMS_R][NMS_TX];
+  const int b = blockIdx.z;
+  const int ox0 = blockIdx.x * NMS_TX, oy0 = blockIdx.y * NMS_TY;
+  const float* hb = heat + (int64_t)b * H * W;
+  constexpr int PW = NMS_TX + 2 * NMS_R, PH = NMS_TY + 2 * NMS_R;
+  for (int idx = threadIdx.x; idx < PW * PH; idx += 256) {
+    const int r = idx / PW, c = idx - r * PW;
+    const int y = oy0 - NMS_R + r, x = ox0 - NMS_R + c;
+    sIn[r][c] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(hb + (int64_t)y * W + x) : -INFINITY;  // MaxPool2d pads with -inf
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < PH * NMS_TX; idx += 256) {
+    const int r = idx / NMS_TX, c = idx - r * NMS_TX;
+    float m = sIn[r][c];
+#pragma unroll
+    for (int d = 1; d <= 2 * NMS_R; ++d) m = fmaxf(m, sIn[r][c + d]);
+    sRow[r][c] = m;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < (NMS_TX * NMS_TY) / 256; ++k) {
+    const int idx = threadIdx.x + 256 * k;
+    const int r = idx / NMS_TX, c = idx - r * NMS_TX;
+    const int x = ox0 + c, y = oy0 + r;
+    float m = sRow[r][c];
+#pragma unroll
+    for (int d = 1; d <= 2 * NMS_R; ++d) m = fmaxf(m, sRow[r + d][c]);
+    const float v = sIn[r + NMS_R][c + NMS_R];
+    const bool pos = (x < W) && (y < H) && (v == m) && (v > thr);
+    bool keep = false;
+    unsigned long long key = 0;
+    if (pos) {
+      // nearest sample of the heat-map at the keypoint itself: round-half-even of x*W/(W-1)-0.5 is x except on the
+      // last row/column, where it falls out of bounds -> 0 (reference quirk).
+      const int xn = (int)rintf(sparse_src_coord(x, W, W));
+      const int yn = (int)rintf(sparse_src_coord(y, H, H));
+      float kv = 0.f;
+      if (xn >= 0 && xn < W && yn >= 0 && yn < H) kv = (xn == x && yn == y) ? v : __ldg(hb + (int64_t)yn * W + xn);
+      // bilinear sample of the 1/8-res reliability map, zeros padding (ATen grid_sampler_2d)
+      const float ix = sparse_src_coord(x, W, Wm), iy = sparse_src_coord(y, H, Hm);
+      const float fx = floorf(ix), fy = floorf(iy);
+      const int x0 = (int)fx, y0 = (int)fy;
+      const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+      const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+      const float* rb = rel + (int64_t)b * Hm * Wm;
+      float bil = 0.f;
+      const bool xin0 = (x0 >= 0 && x0 < Wm), xin1 = (x0 + 1 >= 0 && x0 + 1 < Wm);
+      const bool yin0 = (y0 >= 0 && y0 < Hm), yin1 = (y0 + 1 >= 0 && y0 + 1 < Hm);
+      if (xin0 && yin0) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)y0 * Wm + x0), __fmul_rn(wx0, wy0)));
+      if (xin1 && yin0) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)y0 * Wm + x0 + 1), __fmul_rn(wx1, wy0)));
+      if (xin0 && yin1) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)(y0 + 1) * Wm + x0), __fmul_rn(wx0, wy1)));
+      if (xin1 && yin1) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)(y0 + 1) * Wm + x0 + 1), __fmul_rn(wx1, wy1)));
+      float score = __fmul_rn(kv, bil);
+      if (x == 0 && y == 0) score = -1.f;  // indistinguishable from the zero padding rows (xfeat.py:80)
+      keep = score > 0.f;                  // `valid = scores > 0` (xfeat.py:98) applied early: positives sort first anyway
+      key = ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(y * W + x));
+    }
+    const unsigned mpos = __ballot_sync(0xffffffffu, pos);
+    const unsigned mkeep = __ballot_sync(0xffffffffu, keep);
+    if (mpos && lane == 0) atomicAdd(&n_cand[b], __popc(mpos));
+    if (mkeep) {
+      const int leader = __ffs(mkeep) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&n_keep[b], __popc(mkeep));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (keep) {
+        const int slot = base + __popc(mkeep & ((1u << lane) - 1u));
+        if (slot < cap) keys[(int64_t)b * cap + slot] = key;
+      }
+    }
+  }
+}
+
+__global__ void segment_offsets_kernel(const int* __restrict__ counts, int cap, int B, int* __restrict__ begin,
+                                       int* __restrict__ end) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    begin[b] = b * cap;
+    end[b] = b * cap + min(counts[b], cap);
+  }
+}
+
+__device__ __forceinline__ float cubic1(float x) {  // |x| <= 1, A = -0.75 (ATen cubic_convolution1)
+  const float A = -0.75f;
+  return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+}
+__device__ __forceinline__ float cubic2(float x) {  // 1 < |x| < 2 (ATen cubic_convolution2)
+  const float A = -0.75f;
+  return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+}
+
+// One warp per output slot (b, r). feats: (B,Hm,Wm,64) NHWC un-normalised.
+__global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long long* __restrict__ sorted,
+                                                          const int* __restrict__ n_keep, const float* __restrict__ feats,
+                                                          int B, int H, int W, int Hm, int Wm, int cap, int top_k,
+                                                          float rw, float rh, float* __restrict__ kpts,
+                                                          float* __restrict__ scores, float* __restrict__ desc,
+                                                          int* __restrict__ n_valid, int* __restrict__ kpts_int) {
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= (int64_t)B * top_k) return;
+  const int b = (int)(wid / top_k), r = (int)(wid - (int64_t)b * top_k);
+  const int nv = min(min(n_keep[b], cap), top_k);
+  if (r == 0 && lane == 0) n_valid[b] = nv;
+  float2* dp = reinterpret_cast<float2*>(desc + (wid * 64)) + lane;
+  if (r >= nv) {
+    *dp = make_float2(0.f, 0.f);
+    if (lane == 0) {
+      kpts[wid * 2] = 0.f; kpts[wid * 2 + 1] = 0.f; scores[wid] = 0.f;
+      if (kpts_int) { kpts_int[wid * 2] = 0; kpts_int[wid * 2 + 1] = 0; }
+    }
+    return;
+  }
+  const unsigned long long key = sorted[(int64_t)b * cap + r];
+  const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
+  const int x = (int)(lin % (uint32_t)W), y = (int)(lin / (uint32_t)W);
+  const float ix = sparse_src_coord(x, W, Wm), iy = sparse_src_coord(y, H, Hm);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const float tx = __fsub_rn(ix, fx), ty = __fsub_rn(iy, fy);
+  const int x0 = (int)fx - 1, y0 = (int)fy - 1;
+  const float cx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2((1.f - tx) + 1.f)};
+  const float cy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2((1.f - ty) + 1.f)};
+  const float* fb = feats + (int64_t)b * Hm * Wm * 64;
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int yy = y0 + i;
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xx = x0 + j;
+      float2 v = make_float2(0.f, 0.f);
+      if (yy >= 0 && yy < Hm && xx >= 0 && xx < Wm) {  // warp-uniform
+        v = __ldg(reinterpret_cast<const float2*>(fb + ((int64_t)yy * Wm + xx) * 64) + lane);
+        float ss = v.x * v.x + v.y * v.y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const float den = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(M1, dim=1), xfeat.py:70
+        v.x = __fdiv_rn(v.x, den);
+        v.y = __fdiv_rn(v.y, den);
+      }
+      r0 = fmaf(v.x, cx[j], r0);
+      r1 = fmaf(v.y, cx[j], r1);
+    }
+    o0 = fmaf(r0, cy[i], o0);
+    o1 = fmaf(r1, cy[i], o1);
+  }
+  float ss = o0 * o0 + o1 * o1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float den = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(feats, dim=-1), xfeat.py:93
+  *dp = make_float2(__fdiv_rn(o0, den), __fdiv_rn(o1, den));
+  if (lane == 0) {
+    kpts[wid * 2] = __fmul_rn((float)x, rw);  // mkpts * [rw, rh], xfeat.py:96
+    kpts[wid * 2 + 1] = __fmul_rn((float)y, rh);
+    scores[wid] = ord2f((uint32_t)(key >> 32));
+    if (kpts_int) { kpts_int[wid * 2] = x; kpts_int[wid * 2 + 1] = y; }
+  }
+}
+
+static inline int sparse_cap(int H, int W) { return H * W / 4; }
+
+struct SparseWs {
+  unsigned long long *keys, *sorted;
+  int *n_keep, *n_cand, *seg_begin, *seg_end;
+  void* cub_temp;
+  size_t cub_bytes;
+};
+
+static int carve_sparse(Bump& bump, int B, int H, int W, SparseWs& ws) {
+  const int cap = sparse_cap(H, W);
+  ws.keys = bump.take<unsigned long long>((size_t)B * cap);
+  ws.sorted = bump.take<unsigned long long>((size_t)B * cap);
+  ws.n_keep = bump.take<int>(B);
+  ws.n_cand = bump.take<int>(B);
+  ws.seg_begin = bump.take<int>(B);
+  ws.seg_end = bump.take<int>(B);
+  size_t tb = 0;
+  cudaError_t e = cub::DeviceSegmentedSort::SortKeysDescending(nullptr, tb, (const unsigned long long*)nullptr,
+                                                               (unsigned long long*)nullptr, B * cap, B, (const int*)nullptr,
+                                                               (const int*)nullptr, (cudaStream_t)0);
+  if (e != cudaSuccess) {
+    set_error("cub temp-size query failed: %s", cudaGetErrorString(e));
+    return XF_E_CUDA;
+  }
+  ws.cub_bytes = tb;
+  ws.cub_temp = bump.take<char>(tb);
+  return XF_OK;
+}
+
+}  // namespace xf
+
+extern "C" size_t xfeat_sparse_workspace_bytes(int B, int H, int W, int top_k) {
+  (void)top_k;
+  xf::Bump bump(nullptr, 0);
+  xf::SparseWs ws;
+  if (xf::carve_sparse(bump, B, H, W, ws) != XF_OK) return 0;
+  return bump.used();
+}
+
+extern "C" int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const float* d_heat, const float* d_reliability,
+                                   int B, int H, int W, int top_k, float threshold, float rw, float rh, float* d_kpts,
+                                   float* d_scores, float* d_desc, int32_t* d_n_valid, int32_t* d_n_cand,
+                                   int32_t* d_kpts_int, void* d_ws, size_t ws_bytes, void* stream) {
+  XF_REQUIRE(ctx && d_feats && d_heat && d_reliability && d_kpts && d_scores && d_desc && d_n_valid && d_ws,
+             "detect_sparse: null pointer");
+  XF_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0 && top_k > 0,
+             "detect_sparse: bad shape B=%d H=%d W=%d top_k=%d", B, H, W, top_k);
+  XF_REQUIRE((int64_t)B * xf::sparse_cap(H, W) < (1ll << 31), "detect_sparse: batch too large for 32-bit offsets");
+  XF_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  xf::Bump bump(d_ws, ws_bytes);
+  xf::SparseWs ws;
+  int rc = xf::carve_sparse(bump, B, H, W, ws);
+  if (rc) return rc;
+  if (!bump.ok) {
+    xf::set_error("detect_sparse: workspace too small (%zu < %zu)", ws_bytes, bump.used());
+    return XF_E_WORKSPACE;
+  }
+  const int cap = xf::sparse_cap(H, W), Hm = H / 8, Wm = W / 8;
+  XF_CUDA(cudaMemsetAsync(ws.n_keep, 0, sizeof(int) * B, st));
+  XF_CUDA(cudaMemsetAsync(ws.n_cand, 0, sizeof(int) * B, st));
+  dim3 grid(xf::cdiv(W, xf::NMS_TX), xf::cdiv(H, xf::NMS_TY), B);
+  xf::nms_score_kernel<<<grid, 256, 0, st>>>(d_heat, d_reliability, H, W, Hm, Wm, threshold, cap, ws.keys, ws.n_keep,
+                                             ws.n_cand);
+  XF_LAUNCH_CHECK();
+  xf::segment_offsets_kernel<<<xf::cdiv(B, 128), 128, 0, st>>>(ws.n_keep, cap, B, ws.seg_begin, ws.seg_end);
+  XF_LAUNCH_CHECK();
+  size_t tb = ws.cub_bytes;
+  XF_CUDA(cub::DeviceSegmentedSort::SortKeysDescending(ws.cub_temp, tb, ws.keys, ws.sorted, B * cap, B, ws.seg_begin,
+                                                       ws.seg_end, st));
+  const int64_t warps = (int64_t)B * top_k;
+  xf::sample_desc_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+      ws.sorted, ws.n_keep, d_feats, B, H, W, Hm, Wm, cap, top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid, d_kpts_int);
+  XF_LAUNCH_CHECK();
+  if (d_n_cand) XF_CUDA(cudaMemcpyAsync(d_n_cand, ws.n_cand, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
+  return XF_OK;
+}

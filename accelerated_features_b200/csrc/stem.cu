@@ -1,0 +1,127 @@
+// Stem: block1 (four thin 3x3 convs, 1->4->8->8->24 channels) and skip1 (AvgPool4 + 1x1), model.py:40-48,139-140.
+// GEMM-K is 9/36/72/72: too thin for tensor-core tiles, and the layers are HBM-bound (4-18 FLOP/B),
+// so these are direct convolutions on CUDA cores: one thread per output pixel, all output channels in registers,
+// folded weights passed BY VALUE as a __grid_constant__ kernel parameter so every FFMA reads its weight straight
+// from the constant bank (no shared-memory or register traffic for weights).
+#include "common.cuh"
+
+namespace xf {
+
+template <int CIN, int COUT>
+struct StemW {
+  float w[9 * CIN * COUT];  // [tap][cin][cout]
+  float b[COUT];
+};
+struct SkipW {
+  float w[24];
+  float b[24];
+};
+
+template <int CIN>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&v)[CIN]) {
+  if constexpr (CIN == 1) {
+    v[0] = __ldg(p);
+  } else {
+#pragma unroll
+    for (int i = 0; i < CIN / 4; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+      v[4 * i + 0] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  }
+}
+
+// in: (B,Hi,Wi,CIN) NHWC, out: (B,Ho,Wo,COUT) NHWC, 3x3, pad 1, stride S; out = relu(conv + b) [+ skip].
+template <int CIN, int COUT, int S, bool SKIP>
+__global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ StemW<CIN, COUT> P,
+                                                        const __grid_constant__ SkipW K,
+                                                        const float* __restrict__ in, const float* __restrict__ xn,
+                                                        float* __restrict__ out, int Hi, int Wi, int Ho, int Wo) {
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int oy = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  if (ox >= Wo || oy >= Ho) return;
+  float acc[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+  const float* inb = in + (int64_t)b * Hi * Wi * CIN;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * S - 1 + ky;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * S - 1 + kx;
+      float v[CIN];
+      if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) {
+        load_vec<CIN>(inb + ((int64_t)iy * Wi + ix) * CIN, v);
+      } else {
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) v[ci] = 0.f;
+      }
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co)
+          acc[co] = fmaf(v[ci], P.w[((ky * 3 + kx) * CIN + ci) * COUT + co], acc[co]);
+    }
+  }
+  float skipv = 0.f;
+  if constexpr (SKIP) {
+    // AvgPool2d(4,4) of the normalised gray image (model.py:40), then 1x1 conv 1->24 with bias (model.py:41)
+    const int W0 = Wo * 4;
+    const float* xp = xn + ((int64_t)b * Ho * 4 + oy * 4) * W0 + ox * 4;
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(xp + (int64_t)r * W0));
+      s += t.x; s += t.y; s += t.z; s += t.w;
+    }
+    skipv = s * (1.0f / 16.0f);
+  }
+  float* op = out + (((int64_t)b * Ho + oy) * Wo + ox) * COUT;
+#pragma unroll
+  for (int c4 = 0; c4 < COUT / 4; ++c4) {
+    float r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = 4 * c4 + j;
+      float v = fmaxf(acc[co] + P.b[co], 0.f);
+      if constexpr (SKIP) v += fmaf(skipv, K.w[co], K.b[co]);
+      r[j] = v;
+    }
+    reinterpret_cast<float4*>(op)[c4] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+template <int CIN, int COUT, int S, bool SKIP>
+static int launch_stem(const float* hw, const float* hb, const float* sw, const float* sb, const float* in,
+                       const float* xn, float* out, int B, int Hi, int Wi, cudaStream_t st) {
+  StemW<CIN, COUT> P;
+  memcpy(P.w, hw, sizeof(P.w));
+  memcpy(P.b, hb, sizeof(P.b));
+  SkipW K;
+  memset(&K, 0, sizeof(K));
+  if (SKIP) { memcpy(K.w, sw, sizeof(K.w)); memcpy(K.b, sb, sizeof(K.b)); }
+  const int Ho = Hi / S, Wo = Wi / S;
+  dim3 grid(cdiv(Wo, 32), cdiv(Ho, 4), B);
+  stem_conv_kernel<CIN, COUT, S, SKIP><<<grid, 128, 0, st>>>(P, K, in, xn, out, Hi, Wi, Ho, Wo);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+// xn (B,H,W) -> a1 (B,H,W,4) -> a2 (B,H/2,W/2,8) -> a3 (same,8) -> x1s (B,H/4,W/4,24) = block1(x) + skip1(x)
+int launch_stem_chain(const float* h_weights, const LayerTable& t, const float* xn, float* a1, float* a2, float* a3,
+                      float* x1s, int B, int H, int W, cudaStream_t st) {
+  const float* hw = h_weights;
+  int rc;
+  rc = launch_stem<1, 4, 1, false>(hw + t.w_off[L_B1_0], hw + t.b_off[L_B1_0], nullptr, nullptr, xn, nullptr, a1, B, H, W, st);
+  if (rc) return rc;
+  rc = launch_stem<4, 8, 2, false>(hw + t.w_off[L_B1_1], hw + t.b_off[L_B1_1], nullptr, nullptr, a1, nullptr, a2, B, H, W, st);
+  if (rc) return rc;
+  rc = launch_stem<8, 8, 1, false>(hw + t.w_off[L_B1_2], hw + t.b_off[L_B1_2], nullptr, nullptr, a2, nullptr, a3, B, H / 2, W / 2, st);
+  if (rc) return rc;
+  rc = launch_stem<8, 24, 2, true>(hw + t.w_off[L_B1_3], hw + t.b_off[L_B1_3], hw + t.w_off[L_SKIP1], hw + t.b_off[L_SKIP1],
+                                   a3, xn, x1s, B, H / 2, W / 2, st);
+  return rc;
+}
+
+}  // namespace xf

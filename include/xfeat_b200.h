@@ -1,0 +1,153 @@
+/*
+ * xfeat_b200.h -- C-ABI of libxfeat_sm100.so: the XFeat inference hot path as sm_100a CUDA kernels.
+ *
+ * The reference (verlab/accelerated_features) has no FFI / plugin interface of its own: its boundary is the
+ * Python surface of modules/xfeat.py.  Each entry point below replaces the ATen call
+ * sequence of one reference function; the citation after "replaces:" is the reference file:line.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (PyTorch allocates, we never free it);
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no entry point synchronises
+ *     the device, none allocates device memory except xfeat_create;
+ *   - return value: 0 = ok, otherwise an XF_E_* code; xfeat_last_error() gives the message (thread local);
+ *   - activations are channels-last (NHWC) fp32; the dense feature map returned to the caller is
+ *     (B, H/8, W/8, 64) channels-last, the keypoint heat-map is (B, H, W), reliability is (B, H/8, W/8);
+ *   - H, W below are the network resolution: multiples of 32 (xfeat.py:235-236).
+ */
+#ifndef XFEAT_B200_H
+#define XFEAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XFEAT_ABI_VERSION 1
+#if defined(__GNUC__)
+#define XF_API __attribute__((visibility("default")))
+#else
+#define XF_API
+#endif
+
+enum {
+  XF_OK = 0,
+  XF_E_INVALID = 1,     /* bad argument */
+  XF_E_CUDA = 2,        /* CUDA runtime error (message has the cudaError string) */
+  XF_E_WORKSPACE = 3,   /* workspace too small */
+  XF_E_UNSUPPORTED = 4
+};
+
+/* pixel formats accepted by xfeat_preprocess */
+enum { XF_DTYPE_F32 = 0, XF_DTYPE_U8 = 1 };
+
+typedef struct xfeat_ctx xfeat_ctx;
+
+XF_API int xfeat_abi_version(void);
+XF_API const char* xfeat_last_error(void);
+/* number of kernels of this library launched by the calling process so far (cub sort passes not included) */
+XF_API unsigned long long xfeat_launch_count(void);
+
+/* Number of floats of the packed weight blob expected by xfeat_create (layer table in csrc/layers.h;
+ * accelerated_features_b200/weights.py produces it: BatchNorm folded, [tap][cin][cout] order). */
+XF_API size_t xfeat_packed_weight_floats(void);
+
+/* replaces: XFeat.__init__ / XFeatModel() + load_state_dict (xfeat.py:23-35, model.py:33-111).
+ * `packed_host` is a HOST pointer to xfeat_packed_weight_floats() floats. One ctx per device. */
+XF_API int xfeat_create(xfeat_ctx** out, int device, const float* packed_host, size_t n_floats);
+XF_API void xfeat_destroy(xfeat_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Stage entry points (each is also what the per-kernel parity tests call with oracle tensors)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* replaces: F.interpolate(scale_factor=s, bilinear, align_corners=False) in extract_dualscale (xfeat.py:380-381)
+ * (and parse_input's "/255" when div255 != 0).  Input addressed with element strides like xfeat_preprocess;
+ * output NCHW fp32 (B,C,Ho,Wo) contiguous; source coordinate = (dst+0.5)*scale - 0.5 (clamped at 0), the caller
+ * passes scale = float(1/scale_factor) (ATen area_pixel_compute_scale with a given scale factor). */
+XF_API int xfeat_resize_bilinear(const void* d_in, int dtype, int B, int C, int Hi, int Wi, int64_t stride_b,
+                                 int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255, float* d_out, int Ho,
+                                 int Wo, float scale_h, float scale_w, void* stream);
+
+/* replaces: preprocess_tensor's .float() + F.interpolate(size=(H,W), bilinear) (xfeat.py:233-239) and
+ * XFeatModel.forward's channel mean + InstanceNorm2d(1) (model.py:135-136).
+ * Input: B images, C channels, Hi x Wi pixels, element strides (in elements) for batch/channel/row/col so that
+ * both NCHW tensors and HWC numpy images are read in place.  div255 != 0 applies parse_input's "/255"
+ * (xfeat.py:400-401).  Output d_xn: (B, H, W) fp32 normalised gray.  d_stats: B*2 doubles scratch. */
+XF_API int xfeat_preprocess(const void* d_img, int dtype, int B, int C, int Hi, int Wi,
+                     int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255,
+                     int H, int W, float* d_xn, double* d_stats, void* stream);
+
+XF_API size_t xfeat_net_workspace_bytes(int B, int H, int W);
+/* replaces: XFeatModel.forward (model.py:123-154) minus the normalisation (done by xfeat_preprocess), plus
+ * get_kpts_heatmap (xfeat.py:242-247) fused after keypoint_head.
+ *   d_xn (B,H,W) -> d_feats (B,H/8,W/8,64) NHWC, d_heat (B,H,W), d_reliability (B,H/8,W/8),
+ *   d_kpt_logits (B,H/8,W/8,65) optional (NULL to skip; tests only). */
+XF_API int xfeat_net(xfeat_ctx* ctx, const float* d_xn, int B, int H, int W, float* d_feats, float* d_heat,
+              float* d_reliability, float* d_kpt_logits, void* d_ws, size_t ws_bytes, void* stream);
+
+XF_API size_t xfeat_sparse_workspace_bytes(int B, int H, int W, int top_k);
+/* replaces: F.normalize(M1,dim=1), NMS, nearest*bilinear scores, argsort/top-k, bicubic descriptor sampling,
+ * F.normalize(dim=-1), keypoint rescale and the `scores > 0` filter (xfeat.py:70-103).
+ * Outputs (fixed capacity top_k per image, sorted by score descending, ties by raster index ascending):
+ *   d_kpts (B,top_k,2) f32 = (x*rw, y*rh); d_scores (B,top_k); d_desc (B,top_k,64); d_n_valid (B) int32 = number
+ *   of leading entries with score > 0; d_n_cand (B) int32 = number of NMS maxima above threshold (before the
+ *   score filter; for parity checks, may be NULL); d_kpts_int (B,top_k,2) int32 optional. Entries past n_valid
+ *   are zero-filled. */
+XF_API int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const float* d_heat, const float* d_reliability,
+                        int B, int H, int W, int top_k, float threshold, float rw, float rh,
+                        float* d_kpts, float* d_scores, float* d_desc, int32_t* d_n_valid, int32_t* d_n_cand,
+                        int32_t* d_kpts_int, void* d_ws, size_t ws_bytes, void* stream);
+
+XF_API size_t xfeat_dense_workspace_bytes(int B, int H, int W, int top_k);
+/* replaces: extractDense's topk over the reliability map + gathers + rescale (xfeat.py:366-375) and
+ * extract_dualscale's "/s" (xfeat.py:388).  k = min(top_k, (H/8)*(W/8)).
+ * Writes k rows per image at row offset `out_offset` of outputs with `out_rows` rows per image:
+ *   d_kpts (B,out_rows,2) = (x*8*rw/div_scale, y*8*rh/div_scale); d_desc (B,out_rows,64) un-normalised;
+ *   d_scales (B,out_rows) = scale_value (xfeat.py:389-391; may be NULL); order = reliability descending, ties by cell
+ *   index ascending. d_topk_idx (B,k) int32 optional. */
+XF_API int xfeat_detect_dense(xfeat_ctx* ctx, const float* d_feats, const float* d_reliability, int B, int H, int W,
+                       int top_k, float rw, float rh, float div_scale, float scale_value, int out_rows, int out_offset,
+                       float* d_kpts, float* d_desc, float* d_scales, int32_t* d_topk_idx, void* d_ws, size_t ws_bytes,
+                       void* stream);
+
+XF_API size_t xfeat_mnn_workspace_bytes(int batch, int n1_max, int n2_max);
+/* replaces: XFeat.match (xfeat.py:327-348) and XFeat.batch_match (xfeat.py:265-290).
+ * Batched mutual-nearest-neighbour on dot products: for pair b, rows d_f1 + b*stride1 (n1[b] x 64) against
+ * d_f2 + b*stride2 (n2[b] x 64); strides in floats.  d_n1 / d_n2: device int32 per-pair counts (NULL = n1_max /
+ * n2_max for every pair).  argmax ties resolve to the lowest index, as torch.max / argmax on CPU.
+ * min_cossim <= 0 disables the threshold (reference semantics).
+ * Outputs per pair at capacity n1_max: d_idx0, d_idx1 (batch, n1_max) int64 (idx0 ascending), d_n_matches (batch).
+ * Never materialises the similarity matrix. */
+XF_API int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_max, int64_t stride1,
+                    const float* d_f2, const int32_t* d_n2, int n2_max, int64_t stride2,
+                    int batch, float min_cossim, int64_t* d_idx0, int64_t* d_idx1, int32_t* d_n_matches,
+                    void* d_ws, size_t ws_bytes, void* stream);
+
+/* Gather matched keypoints: out0[b][m] = kpts0[b][idx0[b][m]], out1[b][m] = kpts1[b][idx1[b][m]] for m < n_matches[b]
+ * (replaces the fancy-indexing at xfeat.py:186). kpts are (batch, n_max, 2) f32. */
+XF_API int xfeat_gather_matches(const float* d_kpts0, const float* d_kpts1, int n1_max, int n2_max,
+                         const int64_t* d_idx0, const int64_t* d_idx1, const int32_t* d_n_matches, int batch,
+                         float* d_out0, float* d_out1, void* stream);
+
+XF_API size_t xfeat_refine_workspace_bytes(int batch, int n_max);
+/* replaces: XFeat.refine_matches + fine_matcher + subpix_softmax2d (xfeat.py:292-325, model.py:97-111), for all
+ * pairs of the batch at once.  Inputs: un-normalised coarse descriptors d_desc0/1 (batch,n_max,64), keypoints
+ * d_kpts0/1 (batch,n_max,2), d_scales0 (batch,n_max), coarse matches d_idx0/d_idx1 (batch,n_max) + d_n_matches.
+ * Output d_matches (batch,n_max,4) = (x0+dx*s, y0+dy*s, x1, y1) for rows with conf > fine_conf, order preserved;
+ * d_n_refined (batch). */
+XF_API int xfeat_refine(xfeat_ctx* ctx, const float* d_desc0, const float* d_desc1, const float* d_kpts0,
+                 const float* d_kpts1, const float* d_scales0, const int64_t* d_idx0, const int64_t* d_idx1,
+                 const int32_t* d_n_matches, int batch, int n_max, float fine_conf, float* d_matches,
+                 int32_t* d_n_refined, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Test hook: run one folded conv layer of the packed table (index into csrc/layers.h) through the generic
+ * kernels. in (B,Hi,Wi,Cin) NHWC -> out (B,Ho,Wo,Cout). */
+XF_API int xfeat_debug_conv_layer(xfeat_ctx* ctx, int layer, const float* d_in, int B, int Hi, int Wi, float* d_out,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XFEAT_B200_H */

@@ -1,0 +1,294 @@
+"""GPU parity, stage by stage: every kernel is fed ORACLE tensors of stage i and compared with the oracle's stage
+i+1 (integer outputs exact, floats within the tolerance written beside each check).  Calls go through the C-ABI."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import xfeat_oracle as orc  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def xf():
+    from accelerated_features_b200 import XFeat
+    return XFeat()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from accelerated_features_b200 import _lib
+    return _lib.load()
+
+
+def dev(t):
+    return t.contiguous().cuda()
+
+
+def nhwc(t):  # oracle NCHW -> device NHWC
+    return t.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def relerr(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def vga_batch(assets_vga):
+    ref, tgt = assets_vga
+    return torch.cat([orc.parse_input(ref), orc.parse_input(tgt)], 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_preprocess_identity_u8_and_resize(xf, lib, assets_vga, oracle_state):
+    from accelerated_features_b200 import _lib
+    ref, tgt = assets_vga
+    # (a) uint8 HWC numpy image, /255 applied on device, identity resize
+    x_u8 = torch.from_numpy(np.stack([ref, tgt])).permute(0, 3, 1, 2).cuda()          # strided view of HWC data
+    xn = xf._preprocess(x_u8, 480, 640, div255=True)
+    xo = torch.cat([orc.parse_input(ref), orc.parse_input(tgt)], 0)
+    want = F.instance_norm(xo.mean(dim=1, keepdim=True), eps=1e-5)[:, 0]
+    err = (xn.cpu() - want).abs().max().item()
+    assert err < 2e-5, err                                                           # fp32, |x| <= ~4
+    # (b) float input 300x400 -> 288x384 (bilinear, align_corners=False)
+    crop = np.stack([ref[100:400, 120:520], tgt[100:400, 120:520]])
+    xc = torch.tensor(crop).permute(0, 3, 1, 2).float()
+    xp, rh, rw = orc.preprocess_tensor(xc)
+    want = F.instance_norm(xp.mean(dim=1, keepdim=True), eps=1e-5)[:, 0]
+    xn = xf._preprocess(xc.cuda(), 288, 384, div255=False)
+    err = (xn.cpu() - want).abs().max().item()
+    assert err < 5e-5, err
+
+
+CONV_CASES = [  # (layer id, oracle prefix, is_basic, Hi, Wi, stride, pad)
+    (5, "block2.0", True, 24, 40, 1, 1), (7, "block3.0", True, 24, 40, 2, 1), (8, "block3.1", True, 12, 16, 1, 1),
+    (9, "block3.2", True, 12, 16, 1, 0), (10, "block4.0", True, 20, 80, 2, 1), (11, "block4.1", True, 6, 40, 1, 1),
+    (13, "block5.0", True, 10, 40, 2, 1), (14, "block5.1", True, 5, 20, 1, 1), (16, "block5.3", True, 5, 20, 1, 0),
+    (17, "block_fusion.0", True, 60, 80, 1, 1), (19, "block_fusion.2", False, 12, 16, 1, 0),
+    (8, "block3.1", True, 13, 21, 1, 1),  # ragged: partial tiles in both directions
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: f"L{c[0]}_{c[1]}_{c[3]}x{c[4]}")
+def test_conv_layer_vs_oracle(xf, lib, oracle_state, case):
+    from accelerated_features_b200 import _lib
+    layer, prefix, basic, Hi, Wi, stride, pad = case
+    sd = oracle_state
+    wkey = prefix + (".layer.0.weight" if basic else ".weight")
+    cin = sd[wkey].shape[1]
+    g = torch.Generator().manual_seed(layer * 100 + Hi)
+    x = torch.randn(3, cin, Hi, Wi, generator=g)
+    if basic:
+        want = orc._basic_layer(sd, prefix, x, stride, pad)
+    else:
+        want = F.conv2d(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
+    out = torch.empty((3, want.shape[2], want.shape[3], want.shape[1]), device="cuda")
+    _lib.check(lib.xfeat_debug_conv_layer(xf._ctx, layer, nhwc(x).data_ptr(), 3, Hi, Wi, out.data_ptr(), stream()), "conv")
+    got = out.permute(0, 3, 1, 2).cpu()
+    err = relerr(got, want)
+    assert err < 2e-5, (prefix, err)                                                  # fp32 re-association only
+
+
+@pytest.mark.parametrize("which", ["g3_small", "vga"])
+def test_net_vs_oracle(xf, lib, oracle_state, golden, assets_vga, which):
+    if which == "g3_small":
+        x = torch.from_numpy(golden("g3_randn_small.npz")["x"])
+    else:
+        x = vga_batch(assets_vga)
+    st = orc.backbone(oracle_state, x)
+    B, _, H, W = x.shape
+    feats, heat, rel, logits = xf._run_net(dev(st["xn"][:, 0]), B, H, W, want_logits=True)
+    torch.cuda.synchronize()
+    e_feats = relerr(feats.permute(0, 3, 1, 2).cpu(), st["feats"])
+    e_log = (logits.permute(0, 3, 1, 2).cpu() - st["kpt_logits"]).abs().max().item()
+    e_rel = (rel.cpu() - st["reliability"][:, 0]).abs().max().item()
+    e_heat = (heat.cpu() - orc.kpts_heatmap(st["kpt_logits"])[:, 0]).abs().max().item()
+    print(f"[{which}] feats rel {e_feats:.2e} logits abs {e_log:.2e} reliability abs {e_rel:.2e} heat abs {e_heat:.2e}")
+    assert e_feats < 1e-4 and e_log < 2e-4 and e_rel < 1e-5 and e_heat < 1e-5
+
+
+def canon(kp_xy, scores, W):
+    """order by (score desc, raster index asc) -- the deterministic rule of the CUDA path."""
+    lin = kp_xy[:, 1].astype(np.int64) * W + kp_xy[:, 0].astype(np.int64)
+    return orc.canonical_topk_order(scores, lin)
+
+
+@pytest.mark.parametrize("which,top_k", [("vga", 4096), ("vga", 1000), ("g3_small", 256)])
+def test_detect_sparse_from_oracle_maps(xf, lib, oracle_state, golden, assets_vga, which, top_k):
+    """NMS + score + top-k + bicubic sampling fed with the oracle's feats / heat / reliability."""
+    from accelerated_features_b200 import _lib
+    x = torch.from_numpy(golden("g3_randn_small.npz")["x"]) if which == "g3_small" else vga_batch(assets_vga)
+    res, st = orc.detect_and_compute(oracle_state, x, top_k, 0.05, return_stages=True)
+    B, _, H, W = st["x"].shape
+    feats, heat, rel = nhwc(st["feats"]), dev(st["heat"][:, 0]), dev(st["reliability"][:, 0])
+    kpts = torch.empty((B, top_k, 2), device="cuda"); scores = torch.empty((B, top_k), device="cuda")
+    desc = torch.empty((B, top_k, 64), device="cuda"); nv = torch.empty((B,), dtype=torch.int32, device="cuda")
+    nc = torch.empty((B,), dtype=torch.int32, device="cuda"); ki = torch.empty((B, top_k, 2), dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.xfeat_sparse_workspace_bytes(B, H, W, top_k), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.xfeat_detect_sparse(xf._ctx, feats.data_ptr(), heat.data_ptr(), rel.data_ptr(), B, H, W, top_k, 0.05,
+                                       1.0, 1.0, kpts.data_ptr(), scores.data_ptr(), desc.data_ptr(), nv.data_ptr(),
+                                       nc.data_ptr(), ki.data_ptr(), ws.data_ptr(), ws.numel(), stream()), "detect_sparse")
+    torch.cuda.synchronize()
+    assert nc.tolist() == orc.nms_counts(st["heat"])                                   # NMS maxima count: exact
+    for b in range(B):
+        n = int(nv[b])
+        want_kp = res[b]["keypoints"].numpy(); want_sc = res[b]["scores"].numpy(); want_d = res[b]["descriptors"].numpy()
+        assert n == len(want_kp)
+        got_kp = ki[b, :n].cpu().numpy(); got_sc = scores[b, :n].cpu().numpy(); got_d = desc[b, :n].cpu().numpy()
+        np.testing.assert_allclose(np.sort(got_sc)[::-1], np.sort(want_sc)[::-1], atol=1e-6)   # same score multiset
+        # canonicalise the oracle (its argsort is unstable) and compare element-wise; entries whose score ties with the
+        # cut-off value may legitimately differ in membership
+        o = canon(want_kp, want_sc, W)
+        g = canon(got_kp, got_sc, W)
+        cut = want_sc.min()
+        safe = want_sc[o] > cut + 1e-7
+        assert np.array_equal(got_kp[g][safe], want_kp[o][safe].astype(np.int64)), f"b={b}: keypoint mismatch"
+        np.testing.assert_allclose(got_d[g][safe], want_d[o][safe], atol=2e-5)          # unit-norm fp32 descriptors
+        # our own order must already be canonical
+        assert np.array_equal(g, np.arange(n))
+        # float keypoints = int * (rw, rh) with rw = rh = 1
+        assert np.array_equal(kpts[b, :n].cpu().numpy(), got_kp.astype(np.float32))
+    # padding past n_valid is zero-filled
+    b = 0
+    assert float(desc[b, int(nv[b]):].abs().sum()) == 0.0
+
+
+def run_mnn(xf, f1, f2, thr, n1=None, n2=None):
+    f1c, f2c = f1.cuda().contiguous(), f2.cuda().contiguous()
+    if f1.dim() == 2:
+        i0, i1 = xf.match(f1c, f2c, thr)
+        return i0.cpu().numpy(), i1.cpu().numpy()
+    B = f1.shape[0]
+    n1d = None if n1 is None else torch.tensor(n1, dtype=torch.int32).cuda()
+    n2d = None if n2 is None else torch.tensor(n2, dtype=torch.int32).cuda()
+    idx0, idx1, cnt = xf._mnn_device(f1c, n1d, f1.shape[1], f1.shape[1] * 64, f2c, n2d, f2.shape[1], f2.shape[1] * 64, B, thr)
+    c = cnt.tolist()
+    return [(idx0[b, :c[b]].cpu().numpy(), idx1[b, :c[b]].cpu().numpy()) for b in range(B)]
+
+
+def test_mnn_golden(xf, golden):
+    g = golden("g5_mnn.npz")
+    f1, f2 = torch.from_numpy(g["f1"]), torch.from_numpy(g["f2"])
+    for thr, sfx in ((-1, ""), (0.82, "_082"), (0.3, "_03")):
+        i0, i1 = run_mnn(xf, f1, f2, thr)
+        assert np.array_equal(i0, g["idx0" + sfx]) and np.array_equal(i1, g["idx1" + sfx]), thr
+
+
+def robust_rows(f1, f2, eps=2e-6):
+    """rows / cols whose arg-max is separated from the runner-up by more than fp32 accumulation noise."""
+    rg, cg = orc.mnn_ambiguity(f1, f2)
+    return rg > eps, cg > eps
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (5, 300), (129, 127), (1000, 2048), (4096, 4096), (2500, 777)])
+def test_mnn_vs_oracle_sizes(xf, n1, n2):
+    g = torch.Generator().manual_seed(n1 * 7 + n2)
+    f1 = F.normalize(torch.randn(n1, 64, generator=g), dim=-1)
+    f2 = F.normalize(torch.randn(n2, 64, generator=g), dim=-1)
+    for thr in (-1, 0.3):
+        w0, w1 = orc.mnn_match(f1, f2, thr)
+        i0, i1 = run_mnn(xf, f1, f2, thr)
+        if np.array_equal(i0, w0.numpy()) and np.array_equal(i1, w1.numpy()):
+            continue
+        # any difference must be confined to rows/cols with a near-tie (documented protocol)
+        rok, cok = robust_rows(f1, f2)
+        want = {(int(a), int(b)) for a, b in zip(w0, w1)}
+        got = {(int(a), int(b)) for a, b in zip(i0, i1)}
+        for a, b in want ^ got:
+            assert (not rok[a]) or (not cok[b]), f"robust pair ({a},{b}) differs at thr={thr}"
+
+
+def test_mnn_batched_ragged_and_unnormalised(xf):
+    g = torch.Generator().manual_seed(11)
+    B, N = 5, 700
+    f1 = torch.randn(B, N, 64, generator=g) * 3.0        # star path: raw dot products, not cosine
+    f2 = torch.randn(B, N, 64, generator=g) * 3.0
+    n1 = [700, 1, 128, 333, 0]
+    n2 = [700, 700, 129, 5, 40]
+    got = run_mnn(xf, f1, f2, -1, n1, n2)
+    for b in range(B):
+        if n1[b] == 0 or n2[b] == 0:
+            assert len(got[b][0]) == 0
+            continue
+        w0, w1 = orc.mnn_match(f1[b, :n1[b]], f2[b, :n2[b]], -1)
+        assert np.array_equal(got[b][0], w0.numpy()) and np.array_equal(got[b][1], w1.numpy()), b
+    full = run_mnn(xf, f1, f2, -1)
+    want = orc.batch_match(f1, f2)
+    for b in range(B):
+        assert np.array_equal(full[b][0], want[b][0].numpy()) and np.array_equal(full[b][1], want[b][1].numpy())
+
+
+def test_dense_topk_and_gather_from_oracle_maps(xf, lib, oracle_state, assets_vga):
+    from accelerated_features_b200 import _lib
+    x = vga_batch(assets_vga)
+    x1 = F.interpolate(x, scale_factor=0.6, align_corners=False, mode="bilinear")
+    kp, feats_w, st = orc.extract_dense(oracle_state, x1, 819, return_stages=True)
+    B, _, H, W = st["x"].shape
+    k = 819
+    feats, rel = nhwc(st["feats"]), dev(st["reliability"][:, 0])
+    kpts = torch.empty((B, k, 2), device="cuda"); desc = torch.empty((B, k, 64), device="cuda")
+    sc = torch.empty((B, k), device="cuda"); ti = torch.empty((B, k), dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.xfeat_dense_workspace_bytes(B, H, W, k), dtype=torch.uint8, device="cuda")
+    rh, rw = x1.shape[2] / H, x1.shape[3] / W
+    _lib.check(lib.xfeat_detect_dense(xf._ctx, feats.data_ptr(), rel.data_ptr(), B, H, W, k, float(np.float32(rw)),
+                                      float(np.float32(rh)), 1.0, 1.25, k, 0, kpts.data_ptr(), desc.data_ptr(),
+                                      sc.data_ptr(), ti.data_ptr(), ws.data_ptr(), ws.numel(), stream()), "detect_dense")
+    torch.cuda.synchronize()
+    # torch.topk tie order is unspecified: compare after canonical (value desc, index asc) ordering
+    for b in range(B):
+        v = st["rel_flat"][b].numpy()
+        order = np.lexsort((np.arange(len(v)), -v.astype(np.float64)))[:k]
+        cutv = v[order[-1]]
+        safe = v[order] > cutv
+        assert np.array_equal(ti[b].cpu().numpy()[safe], order[safe])
+        want_kp = (orc.create_xy(H // 8, W // 8) * 8)[order] * torch.tensor([rw, rh])
+        assert np.array_equal(kpts[b].cpu().numpy()[safe], want_kp.numpy()[safe])
+        want_d = st["feats"][b].permute(1, 2, 0).reshape(-1, 64)[order]
+        assert np.array_equal(desc[b].cpu().numpy()[safe], want_d.numpy()[safe])
+    assert float((sc - 1.25).abs().max()) == 0.0
+
+
+def test_refine_from_oracle_coarse(xf, lib, oracle_state, assets_vga):
+    """fine-matcher MLP + softmax expectation + compaction fed with the oracle's coarse features and matches."""
+    x = vga_batch(assets_vga)
+    s1, s2 = x, torch.flip(x, dims=[0])
+    d1 = orc.detect_and_compute_dense(oracle_state, s1, 2000)
+    d2 = orc.detect_and_compute_dense(oracle_state, s2, 2000)
+    idxs = orc.batch_match(d1["descriptors"], d2["descriptors"])
+    B, K, _ = d1["descriptors"].shape
+    idx0 = torch.zeros((B, K), dtype=torch.int64); idx1 = torch.zeros((B, K), dtype=torch.int64)
+    cnt = torch.zeros((B,), dtype=torch.int32)
+    for b in range(B):
+        n = len(idxs[b][0]); cnt[b] = n
+        idx0[b, :n] = idxs[b][0]; idx1[b, :n] = idxs[b][1]
+    dd1 = {k: v.cuda().contiguous() for k, v in d1.items()}
+    dd2 = {k: v.cuda().contiguous() for k, v in d2.items()}
+    matches, n_ref = xf._refine_device(dd1, dd2, idx0.cuda(), idx1.cuda(), cnt.cuda())
+    torch.cuda.synchronize()
+    for b in range(B):
+        want, stg = orc.refine_matches(oracle_state, d1, d2, idxs, b, return_stages=True)
+        conf = stg["conf"].numpy()
+        robust = np.abs(conf - 0.25) > 1e-4                         # rows whose keep/drop decision is not borderline
+        n = int(n_ref[b])
+        got = matches[b, :n].cpu().numpy()
+        if robust.all():
+            assert n == len(want)
+            np.testing.assert_allclose(got, want.numpy(), atol=2e-3)                   # pixels; offsets from a 512-wide MLP
+        else:
+            assert abs(n - len(want)) <= int((~robust).sum())
+
+
+def test_resize_vs_oracle(xf, assets_vga):
+    x = vga_batch(assets_vga)
+    for s in (0.6, 1.3):
+        want = F.interpolate(x, scale_factor=s, align_corners=False, mode="bilinear")
+        got = xf._resize(x.cuda(), False, s).cpu()
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() < 1e-5
