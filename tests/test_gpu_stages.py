@@ -143,16 +143,20 @@ def test_detect_sparse_from_oracle_maps(xf, lib, oracle_state, golden, assets_vg
         assert n == len(want_kp)
         got_kp = ki[b, :n].cpu().numpy(); got_sc = scores[b, :n].cpu().numpy(); got_d = desc[b, :n].cpu().numpy()
         np.testing.assert_allclose(np.sort(got_sc)[::-1], np.sort(want_sc)[::-1], atol=1e-6)   # same score multiset
-        # canonicalise the oracle (its argsort is unstable) and compare element-wise; entries whose score ties with the
-        # cut-off value may legitimately differ in membership
-        o = canon(want_kp, want_sc, W)
-        g = canon(got_kp, got_sc, W)
+        # our own order must already be canonical: score descending, ties by raster index ascending
+        assert np.array_equal(canon(got_kp, got_sc, W), np.arange(n))
+        # the reference's argsort is unstable and scores agree to ~1e-7 only, so positions of near-equal scores may swap:
+        # compare by keypoint identity. Entries whose score ties with the cut-off value may differ in membership.
+        gi = {(int(x), int(y)): i for i, (x, y) in enumerate(got_kp)}
         cut = want_sc.min()
-        safe = want_sc[o] > cut + 1e-7
-        assert np.array_equal(got_kp[g][safe], want_kp[o][safe].astype(np.int64)), f"b={b}: keypoint mismatch"
-        np.testing.assert_allclose(got_d[g][safe], want_d[o][safe], atol=2e-5)          # unit-norm fp32 descriptors
-        # our own order must already be canonical
-        assert np.array_equal(g, np.arange(n))
+        missing = [i for i, (x, y) in enumerate(want_kp) if (int(x), int(y)) not in gi]
+        assert all(want_sc[i] <= cut + 1e-6 for i in missing), f"b={b}: keypoints above the cut-off are missing"
+        assert len(missing) <= 2
+        wi = np.array([i for i in range(n) if i not in set(missing)])
+        gsel = np.array([gi[(int(want_kp[i][0]), int(want_kp[i][1]))] for i in wi])
+        np.testing.assert_allclose(got_sc[gsel], want_sc[wi], atol=1e-6)
+        np.testing.assert_allclose(got_d[gsel], want_d[wi], atol=2e-5)                  # unit-norm fp32 descriptors
+        assert np.abs(gsel - wi).max() <= 8                                             # rank moves only among near-ties
         # float keypoints = int * (rw, rh) with rw = rh = 1
         assert np.array_equal(kpts[b, :n].cpu().numpy(), got_kp.astype(np.float32))
     # padding past n_valid is zero-filled
