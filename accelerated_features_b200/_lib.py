@@ -26,6 +26,8 @@ SIGNATURES = {
     "xfeat_detect_sparse": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "xfeat_dense_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
     "xfeat_detect_dense": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "xfeat_set_mnn_impl": (None, [c_i]),
+    "xfeat_get_mnn_impl": (c_i, []),
     "xfeat_mnn_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "xfeat_mnn_match": (c_i, [c_p, c_p, c_i, c_i64, c_p, c_p, c_i, c_i64, c_i, c_f, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "xfeat_gather_matches": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p]),

@@ -62,9 +62,10 @@ __global__ void __launch_bounds__(256) reliability_kernel(const float* __restric
 }
 
 // keypoint_head.3 (64->65, bias) + softmax over the 65 logits + heat[b, 8h+i, 8w+j] = p[8i+j].
-// One warp per cell, CELLS cells per warp pass; weights [64][65] live in shared memory (stride 65: conflict-free
-// when lanes walk the output-channel axis), the cell's 64 inputs are staged per warp and broadcast.
-constexpr int KPT_WARPS = 8;
+// A warp handles KPT_CPW consecutive cells per pass: their 64-vectors are staged k-major in shared memory so one
+// 128-bit broadcast load feeds 4 cells; weights [64][65] (stride 65: conflict-free along the output-channel axis)
+// are shared by the 4 cells -> 4 LDS per 12 FFMA.
+constexpr int KPT_WARPS = 8, KPT_CPW = 4;
 __global__ void __launch_bounds__(KPT_WARPS * 32) kpt_softmax_kernel(const float* __restrict__ t,
                                                                      const float* __restrict__ w,
                                                                      const float* __restrict__ bias,
@@ -73,47 +74,65 @@ __global__ void __launch_bounds__(KPT_WARPS * 32) kpt_softmax_kernel(const float
                                                                      int64_t ncell) {
   __shared__ float sW[64 * 65];
   __shared__ float sB[65];
-  __shared__ float sT[KPT_WARPS][64];
+  __shared__ __align__(16) float sT[KPT_WARPS][64][KPT_CPW];
   for (int i = threadIdx.x; i < 64 * 65; i += blockDim.x) sW[i] = __ldg(w + i);
   if (threadIdx.x < 65) sB[threadIdx.x] = __ldg(bias + threadIdx.x);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int W = Wc * 8;
-  for (int64_t cell = (int64_t)blockIdx.x * KPT_WARPS + warp; cell < ncell; cell += (int64_t)gridDim.x * KPT_WARPS) {
-    const float2 tv = __ldg(reinterpret_cast<const float2*>(t + cell * 64) + lane);
+  const int64_t ngroup = (ncell + KPT_CPW - 1) / KPT_CPW;
+  for (int64_t grp = (int64_t)blockIdx.x * KPT_WARPS + warp; grp < ngroup; grp += (int64_t)gridDim.x * KPT_WARPS) {
+    const int64_t cell0 = grp * KPT_CPW;
     __syncwarp();
-    sT[warp][2 * lane] = tv.x;
-    sT[warp][2 * lane + 1] = tv.y;
+#pragma unroll
+    for (int c = 0; c < KPT_CPW; ++c) {
+      float2 tv = make_float2(0.f, 0.f);
+      if (cell0 + c < ncell) tv = __ldg(reinterpret_cast<const float2*>(t + (cell0 + c) * 64) + lane);
+      sT[warp][2 * lane][c] = tv.x;
+      sT[warp][2 * lane + 1][c] = tv.y;
+    }
     __syncwarp();
-    float l0 = sB[lane], l1 = sB[lane + 32], l2 = sB[64];
-#pragma unroll 16
+    float l0[KPT_CPW], l1[KPT_CPW], l2[KPT_CPW];
+#pragma unroll
+    for (int c = 0; c < KPT_CPW; ++c) { l0[c] = sB[lane]; l1[c] = sB[lane + 32]; l2[c] = sB[64]; }
+#pragma unroll 8
     for (int k = 0; k < 64; ++k) {
-      const float a = sT[warp][k];
-      l0 = fmaf(a, sW[k * 65 + lane], l0);
-      l1 = fmaf(a, sW[k * 65 + lane + 32], l1);
-      l2 = fmaf(a, sW[k * 65 + 64], l2);
-    }
-    if (logits_out) {
-      float* lo = logits_out + cell * 65;
-      lo[lane] = l0;
-      lo[lane + 32] = l1;
-      if (lane == 0) lo[64] = l2;
-    }
-    float m = fmaxf(fmaxf(l0, l1), l2);
+      const float4 a4 = *reinterpret_cast<const float4*>(&sT[warp][k][0]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float w0 = sW[k * 65 + lane], w1 = sW[k * 65 + lane + 32], w2 = sW[k * 65 + 64];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
-    float s = e0 + e1;
+      for (int c = 0; c < KPT_CPW; ++c) {
+        l0[c] = fmaf(a[c], w0, l0[c]);
+        l1[c] = fmaf(a[c], w1, l1[c]);
+        l2[c] = fmaf(a[c], w2, l2[c]);
+      }
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    s += e2;
-    const int64_t b = cell / ((int64_t)Hc * Wc);
-    const int rem = (int)(cell - b * Hc * Wc);
-    const int h = rem / Wc, wc = rem - h * Wc;
-    // channel c = 8i + j -> pixel (8h+i, 8wc+j): lane -> (i = lane>>3, j = lane&7), second half i += 4
-    float* hp = heat + ((int64_t)b * Hc * 8 + h * 8 + (lane >> 3)) * W + wc * 8 + (lane & 7);
-    hp[0] = e0 / s;
-    hp[(int64_t)4 * W] = e1 / s;
+    for (int c = 0; c < KPT_CPW; ++c) {
+      const int64_t cell = cell0 + c;
+      if (cell >= ncell) break;  // warp-uniform
+      if (logits_out) {
+        float* lo = logits_out + cell * 65;
+        lo[lane] = l0[c];
+        lo[lane + 32] = l1[c];
+        if (lane == 0) lo[64] = l2[c];
+      }
+      float m = fmaxf(fmaxf(l0[c], l1[c]), l2[c]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float e0 = expf(l0[c] - m), e1 = expf(l1[c] - m), e2 = expf(l2[c] - m);
+      float s = e0 + e1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      s += e2;
+      const int64_t b = cell / ((int64_t)Hc * Wc);
+      const int rem = (int)(cell - b * Hc * Wc);
+      const int h = rem / Wc, wc = rem - h * Wc;
+      // channel c = 8i + j -> pixel (8h+i, 8wc+j): lane -> (i = lane>>3, j = lane&7), second half i += 4
+      float* hp = heat + ((int64_t)b * Hc * 8 + h * 8 + (lane >> 3)) * W + wc * 8 + (lane & 7);
+      hp[0] = e0 / s;
+      hp[(int64_t)4 * W] = e1 / s;
+    }
   }
 }
 
@@ -139,7 +158,8 @@ int launch_kpt_softmax(const xfeat_ctx* ctx, const float* t, float* heat, float*
   const float* w = ctx->d_weights + ctx->table.w_off[L_KH_3];
   const float* b = ctx->d_weights + ctx->table.b_off[L_KH_3];
   const int64_t ncell = (int64_t)B * Hc * Wc;
-  const int blocks = (int)std::min<int64_t>((ncell + KPT_WARPS - 1) / KPT_WARPS, (int64_t)ctx->sm_count * 8);
+  const int64_t ngroup = (ncell + KPT_CPW - 1) / KPT_CPW;
+  const int blocks = (int)std::min<int64_t>((ngroup + KPT_WARPS - 1) / KPT_WARPS, (int64_t)ctx->sm_count * 8);
   kpt_softmax_kernel<<<blocks, KPT_WARPS * 32, 0, st>>>(t, w, b, heat, logits, Hc, Wc, ncell);
   XF_LAUNCH_CHECK();
   return XF_OK;

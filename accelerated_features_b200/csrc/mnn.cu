@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(MNN_THREADS) mnn_scan_kernel(const float* __re
 __global__ void __launch_bounds__(1024) mnn_finalize_kernel(const unsigned long long* __restrict__ row_best,
                                                             const unsigned long long* __restrict__ col_best,
                                                             const int* __restrict__ n1p, int n1_max, int n2_max,
-                                                            float min_cossim, long long* __restrict__ idx0,
+                                                            float min_cossim, const float* __restrict__ val_scale,
+                                                            long long* __restrict__ idx0,
                                                             long long* __restrict__ idx1, int* __restrict__ n_matches) {
   using Scan = cub::BlockScan<int, 1024>;
   __shared__ typename Scan::TempStorage tmp;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(1024) mnn_finalize_kernel(const unsigned long 
   const int pair = blockIdx.x;
   const int n1 = n1p ? min(n1p[pair], n1_max) : n1_max;
   if (threadIdx.x == 0) s_base = 0;
+  const float vs = val_scale ? __ldg(val_scale) : 1.0f;   // tensor-core path carries values scaled by a power of two
   __syncthreads();
   for (int i0 = 0; i0 < n1; i0 += 1024) {
     const int i = i0 + threadIdx.x;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(1024) mnn_finalize_kernel(const unsigned long 
         j = packed_idx(rb);
         const unsigned long long cb = col_best[(int64_t)pair * n2_max + j];
         flag = (cb != 0ull) && (packed_idx(cb) == (uint32_t)i);
-        if (min_cossim > 0.f) flag = flag && (packed_val(rb) > min_cossim);
+        if (min_cossim > 0.f) flag = flag && (packed_val(rb) * vs > min_cossim);
       }
     }
     int off, total;
@@ -200,13 +202,24 @@ static void carve_mnn(Bump& bump, int batch, int n1_max, int n2_max, MnnWs& ws) 
   ws.col_best = bump.take<unsigned long long>((size_t)batch * n2_max);
 }
 
+// tensor-core implementation (mnn_tc.cu)
+size_t mnn_tc_workspace_bytes(int batch, int n1_max, int n2_max);
+int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, const float* f2, const int* n2, int n2_max,
+                  int64_t stride2, int batch, void* d_ws, size_t ws_bytes, unsigned long long** best12,
+                  unsigned long long** best21, float** inv_s2, cudaStream_t st);
+static int g_mnn_impl = 1;  // 0 = fp32 CUDA cores, 1 = tcgen05 split-fp16 (default)
+
 }  // namespace xf
+
+extern "C" void xfeat_set_mnn_impl(int impl) { xf::g_mnn_impl = impl ? 1 : 0; }
+extern "C" int xfeat_get_mnn_impl(void) { return xf::g_mnn_impl; }
 
 extern "C" size_t xfeat_mnn_workspace_bytes(int batch, int n1_max, int n2_max) {
   xf::Bump bump(nullptr, 0);
   xf::MnnWs ws;
   xf::carve_mnn(bump, batch, n1_max, n2_max, ws);
-  return bump.used();
+  const size_t a = bump.used(), b = xf::mnn_tc_workspace_bytes(batch, n1_max, n2_max);
+  return a > b ? a : b;
 }
 
 extern "C" int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_max, int64_t stride1, const float* d_f2,
@@ -218,6 +231,17 @@ extern "C" int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_ma
   XF_REQUIRE(((uintptr_t)d_f1 % 16) == 0 && ((uintptr_t)d_f2 % 16) == 0 && stride1 % 4 == 0 && stride2 % 4 == 0,
              "mnn_match: descriptors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (xf::g_mnn_impl == 1) {
+    unsigned long long *b12 = nullptr, *b21 = nullptr;
+    float* inv_s2 = nullptr;
+    int rc = xf::launch_mnn_tc(d_f1, d_n1, n1_max, stride1, d_f2, d_n2, n2_max, stride2, batch, d_ws, ws_bytes, &b12, &b21,
+                               &inv_s2, st);
+    if (rc) return rc;
+    xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(b12, b21, d_n1, n1_max, n2_max, min_cossim, inv_s2, (long long*)d_idx0,
+                                                    (long long*)d_idx1, d_n_matches);
+    XF_LAUNCH_CHECK();
+    return XF_OK;
+  }
   xf::Bump bump(d_ws, ws_bytes);
   xf::MnnWs ws;
   xf::carve_mnn(bump, batch, n1_max, n2_max, ws);
@@ -236,7 +260,7 @@ extern "C" int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_ma
   xf::mnn_scan_kernel<<<grid, xf::MNN_THREADS, xf::MNN_SMEM, st>>>(d_f1, d_n1, n1_max, stride1, d_f2, d_n2, n2_max, stride2,
                                                                   ws.row_best, ws.col_best);
   XF_LAUNCH_CHECK();
-  xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(ws.row_best, ws.col_best, d_n1, n1_max, n2_max, min_cossim,
+  xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(ws.row_best, ws.col_best, d_n1, n1_max, n2_max, min_cossim, nullptr,
                                                   (long long*)d_idx0, (long long*)d_idx1, d_n_matches);
   XF_LAUNCH_CHECK();
   return XF_OK;

@@ -1,0 +1,327 @@
+// Mutual-NN similarity scan on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-equivalent precision.
+//
+// fp32-equivalent via operand splitting: x*s = hi + lo with hi, lo in fp16 (s = power of two chosen from max|x| so that
+// hi uses the fp16 range and lo stays normal), and one K = 192 fp16 GEMM with fp32 accumulation
+//      F1' = [hi1 | hi1 | lo1]   F2' = [hi2 | lo2 | hi2]   =>   F1' F2'^T = hi1.hi2 + hi1.lo2 + lo1.hi2
+// (the dropped lo.lo term is ~2^-22 relative, below fp32 accumulation noise).  The same two arrays serve both scan
+// directions (rows of F1 against F2, rows of F2 against F1): the three K-blocks pair the same factors in the same order,
+// so S12[i][j] and S21[j][i] are bit-identical.
+//
+// One CTA = 256 rows (two M=128 accumulator slabs) x all 128-column tiles of the other set:
+//   warp 0   : TMA producer (A slabs once, then the B tile ring, 128B-swizzled K-major boxes of 64 halves x 128 rows)
+//   warp 1   : TMEM allocation + single-thread tcgen05.mma issue (2 slabs x 12 UMMA 128x128x16 per tile)
+//   warps 2-5: epilogue, one TMEM lane quarter each: tcgen05.ld 32 columns at a time, running row arg-max in registers
+// The accumulators are double buffered in TMEM (2 x 256 columns), so the arg-max of tile t overlaps the MMAs of t+1.
+// Nothing but the final (value, index) per row ever leaves the SM.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace xf {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+constexpr int TC_ROWS = 256, TC_BN = 128, TC_KP = 192, TC_BOX_BYTES = 128 * 128;  // 128 rows x 128 B
+constexpr int TC_THREADS = 192;
+constexpr size_t TC_SMEM = 1024 + 12 * (size_t)TC_BOX_BYTES + 256;
+
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ f, const int* __restrict__ np, int n_max,
+                                                     int64_t stride, unsigned* __restrict__ out) {
+  const int pair = blockIdx.y;
+  const int n = np ? min(np[pair], n_max) : n_max;
+  const float4* p = reinterpret_cast<const float4*>(f + (int64_t)pair * stride);
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * 16; i += gridDim.x * blockDim.x) {
+    const float4 v = __ldg(p + i);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// One warp per row: writes the 192-half split row (second_is_lo = 0: [hi|hi|lo], 1: [hi|lo|hi]); zero rows past n.
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ f, const int* __restrict__ np, int n_max,
+                                                    int n_pad, int64_t stride, const unsigned* __restrict__ absmax,
+                                                    int b_type, __half* __restrict__ out, float* __restrict__ inv_s2) {
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.y;
+  if (wid >= n_pad) return;
+  const int n = np ? min(np[pair], n_max) : n_max;
+  const float mx = __uint_as_float(*absmax);
+  int e = 0;
+  if (mx > 0.f) frexpf(mx, &e);                 // mx = m * 2^e, m in [0.5, 1)  ->  mx < 2^e
+  const float s = (mx > 0.f) ? ldexpf(1.f, 14 - e) : 1.f;   // mx * s in [2^13, 2^14)
+  if (wid == 0 && lane == 0 && pair == 0 && inv_s2) *inv_s2 = (mx > 0.f) ? ldexpf(1.f, 2 * (e - 14)) : 1.f;
+  __half2 hi = __floats2half2_rn(0.f, 0.f), lo = hi;
+  if (wid < n) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(f + (int64_t)pair * stride + wid * 64) + lane);
+    const float x0 = v.x * s, x1 = v.y * s;      // exact (power of two)
+    hi = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hi);
+    lo = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  }
+  __half2* o = reinterpret_cast<__half2*>(out + ((int64_t)pair * n_pad + wid) * TC_KP);
+  o[lane] = hi;
+  o[32 + lane] = b_type ? lo : hi;
+  o[64 + lane] = b_type ? hi : lo;
+}
+
+struct TcMaps {
+  CUtensorMap m1, m2;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_constant__ TcMaps maps,
+                                                               const int* __restrict__ n1p, int n1_max,
+                                                               const int* __restrict__ n2p, int n2_max, int n_pad,
+                                                               unsigned long long* __restrict__ best12,
+                                                               unsigned long long* __restrict__ best21) {
+  const int pair = blockIdx.y, dir = blockIdx.z;
+  const int n1 = n1p ? min(n1p[pair], n1_max) : n1_max;
+  const int n2 = n2p ? min(n2p[pair], n2_max) : n2_max;
+  const int n_rows = dir ? n2 : n1, n_cols = dir ? n1 : n2;
+  const int out_stride = dir ? n2_max : n1_max;
+  unsigned long long* out = dir ? best21 : best12;
+  const CUtensorMap* mapA = dir ? &maps.m2 : &maps.m1;
+  const CUtensorMap* mapB = dir ? &maps.m1 : &maps.m2;
+  const int row0 = blockIdx.x * TC_ROWS;
+  if (row0 >= n_rows) return;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = base;                       // [slab 2][kb 3] boxes
+  unsigned char* sB = base + 6 * TC_BOX_BYTES;    // [stage 2][kb 3] boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 12 * TC_BOX_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;     // [2]
+  uint64_t* b_empty = bars + 3;    // [2]
+  uint64_t* acc_full = bars + 5;   // [2]
+  uint64_t* acc_empty = bars + 7;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (n_cols + TC_BN - 1) / TC_BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(mapA);
+    tc::tma_prefetch_desc(mapB);
+    tc::mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&b_full[i], 1);
+      tc::mbar_init(&b_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      const int arow = pair * n_pad + row0;
+      tc::mbar_expect_tx(a_full, 6 * TC_BOX_BYTES);
+      for (int slab = 0; slab < 2; ++slab)
+        for (int kb = 0; kb < 3; ++kb)
+          tc::tma_load_2d(sA + (slab * 3 + kb) * TC_BOX_BYTES, mapA, a_full, kb * 64, arow + slab * 128);
+      const int brow = pair * n_pad;
+      for (int t = 0; t < T; ++t) {
+        const int s = t & 1;
+        tc::mbar_wait(&b_empty[s], ((t >> 1) & 1) ^ 1);
+        tc::mbar_expect_tx(&b_full[s], 3 * TC_BOX_BYTES);
+        for (int kb = 0; kb < 3; ++kb)
+          tc::tma_load_2d(sB + (s * 3 + kb) * TC_BOX_BYTES, mapB, &b_full[s], kb * 64, brow + t * TC_BN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, TC_BN);
+      tc::mbar_wait(a_full, 0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t & 1, ph = (t >> 1) & 1;
+        tc::mbar_wait(&b_full[s], ph);
+        tc::mbar_wait(&acc_empty[s], ph ^ 1);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int slab = 0; slab < 2; ++slab) {
+          const uint32_t d = tmem + s * 256 + slab * 128;
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + (slab * 3 + kb) * TC_BOX_BYTES), 1024);
+            const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 3 + kb) * TC_BOX_BYTES), 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 16 halves = 32 B = 2 x 16-byte units along K inside the 128 B swizzle row
+              tc::umma_f16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+        }
+        tc::umma_commit(&b_empty[s]);    // B stage may be refilled once these MMAs have read it
+        tc::umma_commit(&acc_full[s]);   // accumulators of tile t are complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: running row arg-max ----------------
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    float best[2] = {-INFINITY, -INFINITY};
+    uint32_t bidx[2] = {0xffffffffu, 0xffffffffu};
+    for (int t = 0; t < T; ++t) {
+      const int s = t & 1, ph = (t >> 1) & 1;
+      tc::mbar_wait(&acc_full[s], ph);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int slab = 0; slab < 2; ++slab) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          __syncwarp();                  // tcgen05.ld is .sync.aligned: reconverge after the data-dependent branch below
+          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + s * 256 + slab * 128 + c * 32, r);
+          tc::tmem_ld_wait();
+          const int col0 = t * TC_BN + c * 32;
+          if (col0 + 32 <= n_cols) {
+            float m = __uint_as_float(r[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+            if (m > best[slab]) {        // strict: earlier columns win ties (torch.max / argmax rule)
+              int j0 = 31;
+#pragma unroll
+              for (int j = 30; j >= 0; --j)
+                if (__uint_as_float(r[j]) == m) j0 = j;
+              best[slab] = m;
+              bidx[slab] = (uint32_t)(col0 + j0);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              if (col0 + j < n_cols && v > best[slab]) { best[slab] = v; bidx[slab] = (uint32_t)(col0 + j); }
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[s]);
+    }
+#pragma unroll
+    for (int slab = 0; slab < 2; ++slab) {
+      const int row = row0 + slab * 128 + q * 32 + lane;
+      if (row < n_rows) out[(int64_t)pair * out_stride + row] = (bidx[slab] == 0xffffffffu) ? 0ull : pack_vi(best[slab], bidx[slab]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, 512);
+  }
+}
+
+struct MnnTcWs {
+  __half *f1s, *f2s;
+  unsigned long long *best12, *best21;
+  unsigned* absmax;
+  float* inv_s2;
+};
+static inline int tc_pad(int n) { return (n + TC_ROWS - 1) / TC_ROWS * TC_ROWS; }
+
+void carve_mnn_tc(Bump& bump, int batch, int n1_max, int n2_max, MnnTcWs& ws) {
+  const int n_pad = tc_pad(n1_max > n2_max ? n1_max : n2_max);
+  ws.f1s = bump.take<__half>((size_t)batch * n_pad * TC_KP);
+  ws.f2s = bump.take<__half>((size_t)batch * n_pad * TC_KP);
+  ws.best12 = bump.take<unsigned long long>((size_t)batch * n1_max);
+  ws.best21 = bump.take<unsigned long long>((size_t)batch * n2_max);
+  ws.absmax = bump.take<unsigned>(1);
+  ws.inv_s2 = bump.take<float>(1);
+}
+
+size_t mnn_tc_workspace_bytes(int batch, int n1_max, int n2_max) {
+  Bump bump(nullptr, 0);
+  MnnTcWs ws;
+  carve_mnn_tc(bump, batch, n1_max, n2_max, ws);
+  return bump.used();
+}
+
+static int make_map(CUtensorMap* m, const __half* ptr, uint64_t rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return XF_E_CUDA;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)TC_KP, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)TC_KP * sizeof(__half)};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return XF_E_CUDA;
+  }
+  return XF_OK;
+}
+
+// Fills best12 (rows of F1 -> arg-max column in F2) and best21 (rows of F2 -> arg-max in F1), packed (value*s^2, index).
+int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, const float* f2, const int* n2, int n2_max,
+                  int64_t stride2, int batch, void* d_ws, size_t ws_bytes, unsigned long long** best12,
+                  unsigned long long** best21, float** inv_s2, cudaStream_t st) {
+  Bump bump(d_ws, ws_bytes);
+  MnnTcWs ws;
+  carve_mnn_tc(bump, batch, n1_max, n2_max, ws);
+  if (!bump.ok) {
+    set_error("mnn_match(tcgen05): workspace too small (%zu < %zu)", ws_bytes, bump.used());
+    return XF_E_WORKSPACE;
+  }
+  const int n_pad = tc_pad(n1_max > n2_max ? n1_max : n2_max);
+  XF_REQUIRE((int64_t)batch * n_pad < (1ll << 31), "mnn_match(tcgen05): batch * n too large");
+  XF_CUDA(cudaMemsetAsync(ws.absmax, 0, sizeof(unsigned), st));
+  absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(f1, n1, n1_max, stride1, ws.absmax);
+  XF_LAUNCH_CHECK();
+  absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(f2, n2, n2_max, stride2, ws.absmax);
+  XF_LAUNCH_CHECK();
+  const dim3 sgrid(cdiv(n_pad * 32, 256), batch);
+  split_kernel<<<sgrid, 256, 0, st>>>(f1, n1, n1_max, n_pad, stride1, ws.absmax, 0, ws.f1s, ws.inv_s2);
+  XF_LAUNCH_CHECK();
+  split_kernel<<<sgrid, 256, 0, st>>>(f2, n2, n2_max, n_pad, stride2, ws.absmax, 1, ws.f2s, nullptr);
+  XF_LAUNCH_CHECK();
+  TcMaps maps;
+  int rc;
+  if ((rc = make_map(&maps.m1, ws.f1s, (uint64_t)batch * n_pad))) return rc;
+  if ((rc = make_map(&maps.m2, ws.f2s, (uint64_t)batch * n_pad))) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    XF_CUDA(cudaFuncSetAttribute(mnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    attr_done = true;
+  }
+  XF_CUDA(cudaMemsetAsync(ws.best12, 0, sizeof(unsigned long long) * (size_t)batch * n1_max, st));
+  XF_CUDA(cudaMemsetAsync(ws.best21, 0, sizeof(unsigned long long) * (size_t)batch * n2_max, st));
+  dim3 grid(n_pad / TC_ROWS, batch, 2);
+  mnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(maps, n1, n1_max, n2, n2_max, n_pad, ws.best12, ws.best21);
+  XF_LAUNCH_CHECK();
+  *best12 = ws.best12;
+  *best21 = ws.best21;
+  *inv_s2 = ws.inv_s2;
+  return XF_OK;
+}
+
+}  // namespace xf

@@ -19,10 +19,13 @@ __global__ void __launch_bounds__(256) nms_score_kernel(const float* __restrict_
                                                         int* __restrict__ n_keep, int* __restrict__ n_cand) {
   __shared__ float sIn[NMS_TY + 2 * NMS_R][NMS_TX + 2 * NMS_R];
   __shared__ float sRow[NMS_TY + 2 * NMS_R][NMS_TX];
+  __shared__ unsigned long long sKeys[NMS_TX * NMS_TY];
+  __shared__ int sCnt[3];  // [0] maxima above threshold, [1] kept (score > 0), [2] global base
   const int b = blockIdx.z;
   const int ox0 = blockIdx.x * NMS_TX, oy0 = blockIdx.y * NMS_TY;
   const float* hb = heat + (int64_t)b * H * W;
   constexpr int PW = NMS_TX + 2 * NMS_R, PH = NMS_TY + 2 * NMS_R;
+  if (threadIdx.x < 3) sCnt[threadIdx.x] = 0;
   for (int idx = threadIdx.x; idx < PW * PH; idx += 256) {
     const int r = idx / PW, c = idx - r * PW;
     const int y = oy0 - NMS_R + r, x = ox0 - NMS_R + c;
@@ -76,20 +79,28 @@ __global__ void __launch_bounds__(256) nms_score_kernel(const float* __restrict_
       keep = score > 0.f;                  // `valid = scores > 0` (xfeat.py:98) applied early: positives sort first anyway
       key = ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(y * W + x));
     }
+    // warp-aggregated append into the CTA-local list (shared-memory atomics), one global atomic per CTA below
     const unsigned mpos = __ballot_sync(0xffffffffu, pos);
     const unsigned mkeep = __ballot_sync(0xffffffffu, keep);
-    if (mpos && lane == 0) atomicAdd(&n_cand[b], __popc(mpos));
+    if (mpos && lane == 0) atomicAdd(&sCnt[0], __popc(mpos));
     if (mkeep) {
       const int leader = __ffs(mkeep) - 1;
       int base = 0;
-      if (lane == leader) base = atomicAdd(&n_keep[b], __popc(mkeep));
+      if (lane == leader) base = atomicAdd(&sCnt[1], __popc(mkeep));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (keep) {
-        const int slot = base + __popc(mkeep & ((1u << lane) - 1u));
-        if (slot < cap) keys[(int64_t)b * cap + slot] = key;
-      }
+      if (keep) sKeys[base + __popc(mkeep & ((1u << lane) - 1u))] = key;
     }
   }
+  __syncthreads();
+  const int nk = sCnt[1];
+  if (threadIdx.x == 0) {
+    if (sCnt[0]) atomicAdd(&n_cand[b], sCnt[0]);
+    sCnt[2] = nk ? atomicAdd(&n_keep[b], nk) : 0;
+  }
+  __syncthreads();
+  const int gbase = sCnt[2];
+  for (int i = threadIdx.x; i < nk; i += 256)
+    if (gbase + i < cap) keys[(int64_t)b * cap + gbase + i] = sKeys[i];
 }
 
 __global__ void segment_offsets_kernel(const int* __restrict__ counts, int cap, int B, int* __restrict__ begin,
@@ -110,72 +121,95 @@ __device__ __forceinline__ float cubic2(float x) {  // 1 < |x| < 2 (ATen cubic_c
   return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
 }
 
-// One warp per output slot (b, r). feats: (B,Hm,Wm,64) NHWC un-normalised.
+// den[p] = max(||feats[p]||_2, 1e-12): the denominator of F.normalize(M1, dim=1) (xfeat.py:70). 8 lanes per pixel.
+__global__ void __launch_bounds__(256) feat_norm_kernel(const float* __restrict__ feats, float* __restrict__ den,
+                                                        int64_t npix) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t pix = gid >> 3;
+  const int sub = (int)(gid & 7);
+  float s = 0.f;
+  if (pix < npix) {
+    const float4* tp = reinterpret_cast<const float4*>(feats + pix * 64) + sub * 2;
+    const float4 a0 = __ldg(tp), a1 = __ldg(tp + 1);
+    s = a0.x * a0.x + a0.y * a0.y + a0.z * a0.z + a0.w * a0.w + a1.x * a1.x + a1.y * a1.y + a1.z * a1.z + a1.w * a1.w;
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (pix < npix && sub == 0) den[pix] = fmaxf(sqrtf(s), 1e-12f);
+}
+
+// Half a warp per output slot (b, r): lane owns 4 channels. feats: (B,Hm,Wm,64) NHWC un-normalised, den: (B,Hm,Wm).
 __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long long* __restrict__ sorted,
                                                           const int* __restrict__ n_keep, const float* __restrict__ feats,
-                                                          int B, int H, int W, int Hm, int Wm, int cap, int top_k,
-                                                          float rw, float rh, float* __restrict__ kpts,
+                                                          const float* __restrict__ den, int B, int H, int W, int Hm, int Wm,
+                                                          int cap, int top_k, float rw, float rh, float* __restrict__ kpts,
                                                           float* __restrict__ scores, float* __restrict__ desc,
                                                           int* __restrict__ n_valid, int* __restrict__ kpts_int) {
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (wid >= (int64_t)B * top_k) return;
-  const int b = (int)(wid / top_k), r = (int)(wid - (int64_t)b * top_k);
+  const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int l16 = threadIdx.x & 15;
+  const int64_t total = (int64_t)B * top_k;
+  const bool live = slot < total;
+  const int64_t sl = live ? slot : total - 1;   // keep the whole warp converged for the shuffles below
+  const int b = (int)(sl / top_k), r = (int)(sl - (int64_t)b * top_k);
   const int nv = min(min(n_keep[b], cap), top_k);
-  if (r == 0 && lane == 0) n_valid[b] = nv;
-  float2* dp = reinterpret_cast<float2*>(desc + (wid * 64)) + lane;
-  if (r >= nv) {
-    *dp = make_float2(0.f, 0.f);
-    if (lane == 0) {
-      kpts[wid * 2] = 0.f; kpts[wid * 2 + 1] = 0.f; scores[wid] = 0.f;
-      if (kpts_int) { kpts_int[wid * 2] = 0; kpts_int[wid * 2 + 1] = 0; }
+  if (live && r == 0 && l16 == 0) n_valid[b] = nv;
+  const bool valid = r < nv;
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  int x = 0, y = 0;
+  unsigned long long key = 0;
+  if (valid) {
+    key = sorted[(int64_t)b * cap + r];
+    const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
+    x = (int)(lin % (uint32_t)W); y = (int)(lin / (uint32_t)W);
+    const float ix = sparse_src_coord(x, W, Wm), iy = sparse_src_coord(y, H, Hm);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float tx = __fsub_rn(ix, fx), ty = __fsub_rn(iy, fy);
+    const int x0 = (int)fx - 1, y0 = (int)fy - 1;
+    const float cx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2((1.f - tx) + 1.f)};
+    const float cy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2((1.f - ty) + 1.f)};
+    const float* fb = feats + (int64_t)b * Hm * Wm * 64;
+    const float* db = den + (int64_t)b * Hm * Wm;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int yy = y0 + i;
+      float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int xx = x0 + j;
+        if (yy >= 0 && yy < Hm && xx >= 0 && xx < Wm) {  // zeros padding
+          const int64_t p = (int64_t)yy * Wm + xx;
+          float4 v = __ldg(reinterpret_cast<const float4*>(fb + p * 64) + l16);
+          const float d = __ldg(db + p);
+          v.x = __fdiv_rn(v.x, d); v.y = __fdiv_rn(v.y, d); v.z = __fdiv_rn(v.z, d); v.w = __fdiv_rn(v.w, d);
+          rr.x = fmaf(v.x, cx[j], rr.x); rr.y = fmaf(v.y, cx[j], rr.y);
+          rr.z = fmaf(v.z, cx[j], rr.z); rr.w = fmaf(v.w, cx[j], rr.w);
+        }
+      }
+      o.x = fmaf(rr.x, cy[i], o.x); o.y = fmaf(rr.y, cy[i], o.y);
+      o.z = fmaf(rr.z, cy[i], o.z); o.w = fmaf(rr.w, cy[i], o.w);
+    }
+  }
+  float ss = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+#pragma unroll
+  for (int s = 8; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+  if (!live) return;
+  float4* dp = reinterpret_cast<float4*>(desc + slot * 64) + l16;
+  if (!valid) {
+    *dp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l16 == 0) {
+      kpts[slot * 2] = 0.f; kpts[slot * 2 + 1] = 0.f; scores[slot] = 0.f;
+      if (kpts_int) { kpts_int[slot * 2] = 0; kpts_int[slot * 2 + 1] = 0; }
     }
     return;
   }
-  const unsigned long long key = sorted[(int64_t)b * cap + r];
-  const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
-  const int x = (int)(lin % (uint32_t)W), y = (int)(lin / (uint32_t)W);
-  const float ix = sparse_src_coord(x, W, Wm), iy = sparse_src_coord(y, H, Hm);
-  const float fx = floorf(ix), fy = floorf(iy);
-  const float tx = __fsub_rn(ix, fx), ty = __fsub_rn(iy, fy);
-  const int x0 = (int)fx - 1, y0 = (int)fy - 1;
-  const float cx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2((1.f - tx) + 1.f)};
-  const float cy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2((1.f - ty) + 1.f)};
-  const float* fb = feats + (int64_t)b * Hm * Wm * 64;
-  float o0 = 0.f, o1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int yy = y0 + i;
-    float r0 = 0.f, r1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int xx = x0 + j;
-      float2 v = make_float2(0.f, 0.f);
-      if (yy >= 0 && yy < Hm && xx >= 0 && xx < Wm) {  // warp-uniform
-        v = __ldg(reinterpret_cast<const float2*>(fb + ((int64_t)yy * Wm + xx) * 64) + lane);
-        float ss = v.x * v.x + v.y * v.y;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        const float den = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(M1, dim=1), xfeat.py:70
-        v.x = __fdiv_rn(v.x, den);
-        v.y = __fdiv_rn(v.y, den);
-      }
-      r0 = fmaf(v.x, cx[j], r0);
-      r1 = fmaf(v.y, cx[j], r1);
-    }
-    o0 = fmaf(r0, cy[i], o0);
-    o1 = fmaf(r1, cy[i], o1);
-  }
-  float ss = o0 * o0 + o1 * o1;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float den = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(feats, dim=-1), xfeat.py:93
-  *dp = make_float2(__fdiv_rn(o0, den), __fdiv_rn(o1, den));
-  if (lane == 0) {
-    kpts[wid * 2] = __fmul_rn((float)x, rw);  // mkpts * [rw, rh], xfeat.py:96
-    kpts[wid * 2 + 1] = __fmul_rn((float)y, rh);
-    scores[wid] = ord2f((uint32_t)(key >> 32));
-    if (kpts_int) { kpts_int[wid * 2] = x; kpts_int[wid * 2 + 1] = y; }
+  const float dn = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(feats, dim=-1), xfeat.py:93
+  *dp = make_float4(__fdiv_rn(o.x, dn), __fdiv_rn(o.y, dn), __fdiv_rn(o.z, dn), __fdiv_rn(o.w, dn));
+  if (l16 == 0) {
+    kpts[slot * 2] = __fmul_rn((float)x, rw);  // mkpts * [rw, rh], xfeat.py:96
+    kpts[slot * 2 + 1] = __fmul_rn((float)y, rh);
+    scores[slot] = ord2f((uint32_t)(key >> 32));
+    if (kpts_int) { kpts_int[slot * 2] = x; kpts_int[slot * 2 + 1] = y; }
   }
 }
 
@@ -184,6 +218,7 @@ static inline int sparse_cap(int H, int W) { return H * W / 4; }
 struct SparseWs {
   unsigned long long *keys, *sorted;
   int *n_keep, *n_cand, *seg_begin, *seg_end;
+  float* den;
   void* cub_temp;
   size_t cub_bytes;
 };
@@ -196,6 +231,7 @@ static int carve_sparse(Bump& bump, int B, int H, int W, SparseWs& ws) {
   ws.n_cand = bump.take<int>(B);
   ws.seg_begin = bump.take<int>(B);
   ws.seg_end = bump.take<int>(B);
+  ws.den = bump.take<float>((size_t)B * (H / 8) * (W / 8));
   size_t tb = 0;
   cudaError_t e = cub::DeviceSegmentedSort::SortKeysDescending(nullptr, tb, (const unsigned long long*)nullptr,
                                                                (unsigned long long*)nullptr, B * cap, B, (const int*)nullptr,
@@ -250,9 +286,13 @@ extern "C" int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const f
   size_t tb = ws.cub_bytes;
   XF_CUDA(cub::DeviceSegmentedSort::SortKeysDescending(ws.cub_temp, tb, ws.keys, ws.sorted, B * cap, B, ws.seg_begin,
                                                        ws.seg_end, st));
-  const int64_t warps = (int64_t)B * top_k;
-  xf::sample_desc_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-      ws.sorted, ws.n_keep, d_feats, B, H, W, Hm, Wm, cap, top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid, d_kpts_int);
+  const int64_t npix = (int64_t)B * Hm * Wm;
+  xf::feat_norm_kernel<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, st>>>(d_feats, ws.den, npix);
+  XF_LAUNCH_CHECK();
+  const int64_t slots = (int64_t)B * top_k;
+  xf::sample_desc_kernel<<<(unsigned)((slots * 16 + 255) / 256), 256, 0, st>>>(
+      ws.sorted, ws.n_keep, d_feats, ws.den, B, H, W, Hm, Wm, cap, top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid,
+      d_kpts_int);
   XF_LAUNCH_CHECK();
   if (d_n_cand) XF_CUDA(cudaMemcpyAsync(d_n_cand, ws.n_cand, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
   return XF_OK;

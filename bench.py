@@ -258,6 +258,9 @@ def run_gpu(args):
         flops = 2.0 * 64.0 * float((out[3].double() * out[4].double()).sum())
         achieved = flops / (mnn_ms / 1e3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        tc = lib.xfeat_get_mnn_impl() == 1
+        kname = ("mnn_tc_kernel (tcgen05 split-fp16 K=192 D1.D2^T, fp32 accumulate in TMEM, fused row arg-max, both directions; "
+                 "timed call also contains absmax/split/finalize)") if tc else "mnn_scan_kernel (fp32 FFMA D1.D2^T + fused row/col arg-max)"
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -268,7 +271,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(2 * r0.numel() * 4 + rc.numel() * 4), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "mnn_scan_kernel (fp32 FFMA D1.D2^T + fused row/col arg-max)", "bound": "tensor",
+            "roofline": {"kernel": kname, "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_kind": f"{pk_kind} bf16 dense, sustained", "ms_per_launch": mnn_ms, "traffic": None},
         }

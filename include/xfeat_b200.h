@@ -112,6 +112,10 @@ XF_API int xfeat_detect_dense(xfeat_ctx* ctx, const float* d_feats, const float*
                        float* d_kpts, float* d_desc, float* d_scales, int32_t* d_topk_idx, void* d_ws, size_t ws_bytes,
                        void* stream);
 
+/* Implementation switch of xfeat_mnn_match (process-wide): 0 = fp32 CUDA-core kernel, 1 = tcgen05 tensor-core kernel
+ * (split-fp16 operands, fp32 accumulation in TMEM). Both honour the same tie rule. */
+XF_API void xfeat_set_mnn_impl(int impl);
+XF_API int xfeat_get_mnn_impl(void);
 XF_API size_t xfeat_mnn_workspace_bytes(int batch, int n1_max, int n2_max);
 /* replaces: XFeat.match (xfeat.py:327-348) and XFeat.batch_match (xfeat.py:265-290).
  * Batched mutual-nearest-neighbour on dot products: for pair b, rows d_f1 + b*stride1 (n1[b] x 64) against

@@ -1,0 +1,126 @@
+"""tcgen05 (tensor-core, split-fp16) implementation of xfeat_mnn_match against the CPU oracle.
+
+The tensor-core scan computes S = hi.hi + hi.lo + lo.hi with fp32 accumulation: agreement with the fp32 oracle is exact
+except where the arg-max is separated from the runner-up by less than accumulation noise; any difference must be
+confined to such near-tie rows / columns (documented protocol)."""
+import contextlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import xfeat_oracle as orc  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def xf():
+    from accelerated_features_b200 import XFeat
+    return XFeat()
+
+
+@contextlib.contextmanager
+def mnn_impl(xf, impl):
+    old = xf._lib.xfeat_get_mnn_impl()
+    xf._lib.xfeat_set_mnn_impl(impl)
+    try:
+        yield
+    finally:
+        xf._lib.xfeat_set_mnn_impl(old)
+
+
+def check_modulo_ties(f1, f2, got, want, eps_rel=3e-6):
+    g0, g1 = got
+    w0, w1 = want
+    if np.array_equal(g0, w0) and np.array_equal(g1, w1):
+        return 0
+    s = f1.double() @ f2.double().t()
+    eps = eps_rel * float(s.abs().max())
+    r = torch.topk(s, min(2, s.shape[1]), dim=1).values
+    c = torch.topk(s, min(2, s.shape[0]), dim=0).values
+    rgap = (r[:, 0] - r[:, -1]) if s.shape[1] > 1 else torch.full((s.shape[0],), 1e9)
+    cgap = (c[0] - c[-1]) if s.shape[0] > 1 else torch.full((s.shape[1],), 1e9)
+    wset = {(int(a), int(b)) for a, b in zip(w0, w1)}
+    gset = {(int(a), int(b)) for a, b in zip(g0, g1)}
+    diff = wset ^ gset
+    for a, b in diff:
+        assert rgap[a] < eps or cgap[b] < eps, f"robust pair ({a},{b}) differs (row gap {float(rgap[a]):.3e}, col gap {float(cgap[b]):.3e}, eps {eps:.3e})"
+    return len(diff)
+
+
+def run(xf, f1, f2, thr):
+    i0, i1 = xf.match(f1.cuda(), f2.cuda(), thr)
+    return i0.cpu().numpy(), i1.cpu().numpy()
+
+
+def test_tc_golden(xf, golden):
+    g = golden("g5_mnn.npz")
+    f1, f2 = torch.from_numpy(g["f1"]), torch.from_numpy(g["f2"])
+    with mnn_impl(xf, 1):
+        for thr, sfx in ((-1, ""), (0.82, "_082"), (0.3, "_03")):
+            got = run(xf, f1, f2, thr)
+            nd = check_modulo_ties(f1, f2, got, (g["idx0" + sfx], g["idx1" + sfx]))
+            print(f"thr={thr}: {len(got[0])} matches, {nd} tie-differences")
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (5, 300), (129, 127), (256, 256), (257, 511), (1000, 2048), (4096, 4096), (2500, 777)])
+def test_tc_vs_oracle_sizes(xf, n1, n2):
+    g = torch.Generator().manual_seed(n1 * 7 + n2)
+    f1 = F.normalize(torch.randn(n1, 64, generator=g), dim=-1)
+    f2 = F.normalize(torch.randn(n2, 64, generator=g), dim=-1)
+    with mnn_impl(xf, 1):
+        for thr in (-1, 0.3):
+            w0, w1 = orc.mnn_match(f1, f2, thr)
+            got = run(xf, f1, f2, thr)
+            nd = check_modulo_ties(f1, f2, got, (w0.numpy(), w1.numpy()))
+            assert nd <= max(2, n1 // 500)
+
+
+def test_tc_equals_simt_on_real_descriptors(xf, assets_vga):
+    """Descriptors of the asset pair: both implementations must return the same matches (modulo near-ties)."""
+    ref, tgt = assets_vga
+    out = xf.detectAndCompute(np.stack([ref, tgt]).transpose(0, 3, 1, 2).astype(np.float32) / 255, top_k=4096) \
+        if False else xf.detectAndCompute(torch.from_numpy(np.stack([ref, tgt])).permute(0, 3, 1, 2).float() / 255, top_k=4096)
+    d0, d1 = out[0]["descriptors"], out[1]["descriptors"]
+    with mnn_impl(xf, 0):
+        a0, a1 = xf.match(d0, d1, -1)
+    with mnn_impl(xf, 1):
+        b0, b1 = xf.match(d0, d1, -1)
+        c0, c1 = xf.match(d0, d1, 0.82)
+    nd = check_modulo_ties(d0.cpu(), d1.cpu(), (b0.cpu().numpy(), b1.cpu().numpy()), (a0.cpu().numpy(), a1.cpu().numpy()))
+    print(f"asset pair: simt {len(a0)} matches, tcgen05 {len(b0)}, differing pairs {nd}; 0.82 -> {len(c0)}")
+    w0, w1 = orc.mnn_match(d0.cpu(), d1.cpu(), 0.82)
+    check_modulo_ties(d0.cpu(), d1.cpu(), (c0.cpu().numpy(), c1.cpu().numpy()), (w0.numpy(), w1.numpy()))
+    assert nd <= 4
+
+
+def test_tc_batched_ragged_unnormalised(xf):
+    g = torch.Generator().manual_seed(11)
+    B, N = 5, 700
+    f1 = torch.randn(B, N, 64, generator=g) * 3.0
+    f2 = torch.randn(B, N, 64, generator=g) * 3.0
+    n1 = [700, 1, 128, 333, 0]
+    n2 = [700, 700, 129, 5, 40]
+    with mnn_impl(xf, 1):
+        idx0, idx1, cnt = xf._mnn_device(f1.cuda(), torch.tensor(n1, dtype=torch.int32).cuda(), N, N * 64, f2.cuda(),
+                                         torch.tensor(n2, dtype=torch.int32).cuda(), N, N * 64, B, -1)
+    c = cnt.tolist()
+    for b in range(B):
+        if n1[b] == 0 or n2[b] == 0:
+            assert c[b] == 0
+            continue
+        w0, w1 = orc.mnn_match(f1[b, :n1[b]], f2[b, :n2[b]], -1)
+        check_modulo_ties(f1[b, :n1[b]], f2[b, :n2[b]], (idx0[b, :c[b]].cpu().numpy(), idx1[b, :c[b]].cpu().numpy()),
+                          (w0.numpy(), w1.numpy()))
+
+
+def test_tc_full_size_identity(xf):
+    """64 x (4096 x 4096): matching a set against itself returns the identity (size-independent property)."""
+    g = torch.Generator().manual_seed(5)
+    f = F.normalize(torch.randn(64, 4096, 64, generator=g), dim=-1).cuda()
+    with mnn_impl(xf, 1):
+        idx0, idx1, cnt = xf._mnn_device(f, None, 4096, 4096 * 64, f, None, 4096, 4096 * 64, 64, -1)
+    assert cnt.tolist() == [4096] * 64
+    assert torch.equal(idx0, idx1) and torch.equal(idx0[3], torch.arange(4096, device="cuda"))
