@@ -20,6 +20,8 @@ SIGNATURES = {
     "xfeat_destroy": (None, [c_p]),
     "xfeat_resize_bilinear": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i64, c_i64, c_i64, c_i64, c_i, c_p, c_i, c_i, c_f, c_f, c_p]),
     "xfeat_preprocess": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i64, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "xfeat_set_conv_impl": (None, [c_i]),
+    "xfeat_get_conv_impl": (c_i, []),
     "xfeat_net_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "xfeat_net": (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "xfeat_sparse_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
@@ -34,6 +36,7 @@ SIGNATURES = {
     "xfeat_refine_workspace_bytes": (c_sz, [c_i, c_i]),
     "xfeat_refine": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_sz, c_p]),
     "xfeat_debug_conv_layer": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_p]),
+    "xfeat_debug_conv_layer_tc": (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_p, c_sz, c_p]),
 }
 
 

@@ -9,6 +9,7 @@ namespace xf {
 
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
+static int g_conv_impl = 1;  // 0 = fp32 CUDA-core convs everywhere, 1 = tcgen05 for the 64->64 stride-1 layers (default)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -81,14 +82,27 @@ extern "C" int xfeat_create(xfeat_ctx** out, int device, const float* packed_hos
     delete c;
     return XF_E_CUDA;
   }
+  c->d_tcw = nullptr;
+  const int rc = xf::conv_tc_prepare(c);
+  if (rc != XF_OK) {
+    cudaFree(c->d_weights);
+    if (c->d_tcw) cudaFree(c->d_tcw);
+    free(c->h_weights);
+    delete c;
+    return rc;
+  }
   *out = c;
   return XF_OK;
 }
+
+extern "C" void xfeat_set_conv_impl(int impl) { xf::g_conv_impl = impl ? 1 : 0; }
+extern "C" int xfeat_get_conv_impl(void) { return xf::g_conv_impl; }
 
 extern "C" void xfeat_destroy(xfeat_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->d_weights) cudaFree(ctx->d_weights);
+  if (ctx->d_tcw) cudaFree(ctx->d_tcw);
   free(ctx->h_weights);
   delete ctx;
 }
@@ -123,33 +137,59 @@ extern "C" int xfeat_net(xfeat_ctx* ctx, const float* d_xn, int B, int H, int W,
   // block2                                                                       model.py:140
   XF_RUN(launch_conv_layer(ctx, L_B2_0, ws.x1s, IN_NHWC, B, H4, W4, ws.t4a, st));
   XF_RUN(launch_conv_layer(ctx, L_B2_1, ws.t4a, IN_NHWC, B, H4, W4, ws.x2, st));
-  // block3                                                                       model.py:141
-  XF_RUN(launch_conv_layer(ctx, L_B3_0, ws.x2, IN_NHWC, B, H4, W4, ws.t8a, st));
-  XF_RUN(launch_conv_layer(ctx, L_B3_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
-  XF_RUN(launch_conv_layer(ctx, L_B3_2, ws.t8b, IN_NHWC, B, H8, W8, ws.x3, st));
-  // block4                                                                       model.py:142
-  XF_RUN(launch_conv_layer(ctx, L_B4_0, ws.x3, IN_NHWC, B, H8, W8, ws.t16a, st));
-  XF_RUN(launch_conv_layer(ctx, L_B4_1, ws.t16a, IN_NHWC, B, H16, W16, ws.t16b, st));
-  XF_RUN(launch_conv_layer(ctx, L_B4_2, ws.t16b, IN_NHWC, B, H16, W16, ws.x4, st));
+  if (g_conv_impl == 0) {
+    // ------------------------------ all layers on the fp32 CUDA-core kernels ------------------------------
+    XF_RUN(launch_conv_layer(ctx, L_B3_0, ws.x2, IN_NHWC, B, H4, W4, ws.t8a, st));
+    XF_RUN(launch_conv_layer(ctx, L_B3_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
+    XF_RUN(launch_conv_layer(ctx, L_B3_2, ws.t8b, IN_NHWC, B, H8, W8, ws.x3, st));
+    XF_RUN(launch_conv_layer(ctx, L_B4_0, ws.x3, IN_NHWC, B, H8, W8, ws.t16a, st));
+    XF_RUN(launch_conv_layer(ctx, L_B4_1, ws.t16a, IN_NHWC, B, H16, W16, ws.t16b, st));
+    XF_RUN(launch_conv_layer(ctx, L_B4_2, ws.t16b, IN_NHWC, B, H16, W16, ws.x4, st));
+  } else {
+    // ------------- 64->64 stride-1 layers on tcgen05; activations between them travel as split fp16 -------------
+    __half *s8a = (__half*)ws.t8a, *s8b = (__half*)ws.t8b, *s16a = (__half*)ws.t16a, *s16b = (__half*)ws.t16b;
+    XF_RUN(launch_conv_layer(ctx, L_B3_0, ws.x2, IN_NHWC, B, H4, W4, nullptr, st, nullptr, s8a));   // block3, model.py:141
+    XF_RUN(launch_conv_tc(ctx, L_B3_1, s8a, B, H8, W8, s8b, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_B3_2, s8b, B, H8, W8, nullptr, ws.x3, st));
+    XF_RUN(launch_conv_layer(ctx, L_B4_0, ws.x3, IN_NHWC, B, H8, W8, nullptr, st, nullptr, s16a));  // block4, model.py:142
+    XF_RUN(launch_conv_tc(ctx, L_B4_1, s16a, B, H16, W16, s16b, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_B4_2, s16b, B, H16, W16, nullptr, ws.x4, st));
+  }
   // block5                                                                       model.py:143
   XF_RUN(launch_conv_layer(ctx, L_B5_0, ws.x4, IN_NHWC, B, H16, W16, ws.t32a, st));
   XF_RUN(launch_conv_layer(ctx, L_B5_1, ws.t32a, IN_NHWC, B, H32, W32, ws.t32b, st));
   XF_RUN(launch_conv_layer(ctx, L_B5_2, ws.t32b, IN_NHWC, B, H32, W32, ws.t32a, st));
   XF_RUN(launch_conv_layer(ctx, L_B5_3, ws.t32a, IN_NHWC, B, H32, W32, ws.x5, st));
-  // pyramid fusion                                                               model.py:146-148
-  XF_RUN(launch_fuse_pyramid(ws.x3, ws.x4, ws.x5, ws.fin, B, H8, W8, st));
-  XF_RUN(launch_conv_layer(ctx, L_FU_0, ws.fin, IN_NHWC, B, H8, W8, ws.f1, st));
-  XF_RUN(launch_conv_layer(ctx, L_FU_1, ws.f1, IN_NHWC, B, H8, W8, ws.f2, st));
-  XF_RUN(launch_conv_layer(ctx, L_FU_2, ws.f2, IN_NHWC, B, H8, W8, d_feats, st));
-  // reliability head                                                             model.py:151
-  XF_RUN(launch_conv_layer(ctx, L_HH_0, d_feats, IN_NHWC, B, H8, W8, ws.t8a, st));
-  XF_RUN(launch_conv_layer(ctx, L_HH_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
-  XF_RUN(launch_reliability(ctx, ws.t8b, d_reliability, (int64_t)B * H8 * W8, st));
-  // keypoint head on the 8x8-unfolded gray image, softmax + depth-to-space        model.py:152, xfeat.py:242-247
-  XF_RUN(launch_conv_layer(ctx, L_KH_0, d_xn, IN_UNFOLD8, B, H8, W8, ws.t8a, st));
-  XF_RUN(launch_conv_layer(ctx, L_KH_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
-  XF_RUN(launch_conv_layer(ctx, L_KH_2, ws.t8b, IN_NHWC, B, H8, W8, ws.t8a, st));
-  XF_RUN(launch_kpt_softmax(ctx, ws.t8a, d_heat, d_kpt_logits, B, H8, W8, st));
+  if (g_conv_impl == 0) {
+    // pyramid fusion                                                             model.py:146-148
+    XF_RUN(launch_fuse_pyramid(ws.x3, ws.x4, ws.x5, ws.fin, nullptr, B, H8, W8, st));
+    XF_RUN(launch_conv_layer(ctx, L_FU_0, ws.fin, IN_NHWC, B, H8, W8, ws.f1, st));
+    XF_RUN(launch_conv_layer(ctx, L_FU_1, ws.f1, IN_NHWC, B, H8, W8, ws.f2, st));
+    XF_RUN(launch_conv_layer(ctx, L_FU_2, ws.f2, IN_NHWC, B, H8, W8, d_feats, st));
+    // reliability head                                                           model.py:151
+    XF_RUN(launch_conv_layer(ctx, L_HH_0, d_feats, IN_NHWC, B, H8, W8, ws.t8a, st));
+    XF_RUN(launch_conv_layer(ctx, L_HH_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
+    XF_RUN(launch_reliability(ctx, ws.t8b, d_reliability, (int64_t)B * H8 * W8, st));
+    // keypoint head on the 8x8-unfolded gray image, softmax + depth-to-space      model.py:152, xfeat.py:242-247
+    XF_RUN(launch_conv_layer(ctx, L_KH_0, d_xn, IN_UNFOLD8, B, H8, W8, ws.t8a, st));
+    XF_RUN(launch_conv_layer(ctx, L_KH_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
+    XF_RUN(launch_conv_layer(ctx, L_KH_2, ws.t8b, IN_NHWC, B, H8, W8, ws.t8a, st));
+    XF_RUN(launch_kpt_softmax(ctx, ws.t8a, d_heat, d_kpt_logits, B, H8, W8, st));
+  } else {
+    __half *s8a = (__half*)ws.t8a, *s8b = (__half*)ws.t8b, *sfin = (__half*)ws.fin, *sf1 = (__half*)ws.f1, *sf2 = (__half*)ws.f2;
+    XF_RUN(launch_fuse_pyramid(ws.x3, ws.x4, ws.x5, nullptr, sfin, B, H8, W8, st));                 // model.py:146-148
+    XF_RUN(launch_conv_tc(ctx, L_FU_0, sfin, B, H8, W8, sf1, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_FU_1, sf1, B, H8, W8, sf2, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_FU_2, sf2, B, H8, W8, s8a, d_feats, st));      // fp32 feats for the samplers + split for the head
+    XF_RUN(launch_conv_tc(ctx, L_HH_0, s8a, B, H8, W8, s8b, nullptr, st));                          // model.py:151
+    XF_RUN(launch_conv_tc(ctx, L_HH_1, s8b, B, H8, W8, nullptr, ws.t8a, st));
+    XF_RUN(launch_reliability(ctx, ws.t8a, d_reliability, (int64_t)B * H8 * W8, st));
+    XF_RUN(launch_unfold8_split(d_xn, s8b, B, H8, W8, st));                                          // model.py:152
+    XF_RUN(launch_conv_tc(ctx, L_KH_0, s8b, B, H8, W8, s8a, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_KH_1, s8a, B, H8, W8, s8b, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_KH_2, s8b, B, H8, W8, nullptr, ws.t8a, st));
+    XF_RUN(launch_kpt_softmax(ctx, ws.t8a, d_heat, d_kpt_logits, B, H8, W8, st));
+  }
 #undef XF_RUN
   return XF_OK;
 }

@@ -1,5 +1,7 @@
 // Shared helpers for libxfeat_sm100.so (sm_100a only).
 #pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -118,17 +120,28 @@ struct xfeat_ctx {
   float* d_weights;     // packed blob on device
   float* h_weights;     // host copy (stem weights travel as kernel parameters)
   xf::LayerTable table; // offsets into d_weights
+  // tensor-core path (conv_tc.cu): pre-split fp16 weights [tap][term][cout][cin], their TMA maps, 2^-k rescale
+  void* d_tcw;
+  size_t tc_off[xf::L_COUNT];
+  float tc_inv_wscale[xf::L_COUNT];
+  CUtensorMap tc_wmap[xf::L_COUNT];
 };
 
 // ---- stage launchers shared between translation units -------------------------------------------------
 namespace xf {
 enum { IN_NHWC = 0, IN_UNFOLD8 = 1 };
 int launch_conv_layer(const xfeat_ctx* ctx, int layer, const float* in, int in_mode, int B, int Hi, int Wi,
-                      float* out, cudaStream_t st, const int* n_live = nullptr);
+                      float* out, cudaStream_t st, const int* n_live = nullptr, __half* out_split = nullptr);
+bool conv_tc_eligible(int layer);
+int conv_tc_prepare(xfeat_ctx* ctx);
+int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int H, int W, __half* out_split,
+                   float* out_f32, cudaStream_t st);
+int launch_split_nhwc64(const float* in, __half* out, int64_t npix, cudaStream_t st);
+int launch_unfold8_split(const float* xn, __half* out, int B, int Hc, int Wc, cudaStream_t st);
 int launch_stem_chain(const float* h_weights, const LayerTable& t, const float* xn, float* a1, float* a2, float* a3,
                       float* x1s, int B, int H, int W, cudaStream_t st);
-int launch_fuse_pyramid(const float* x3, const float* x4, const float* x5, float* out, int B, int H3, int W3,
-                        cudaStream_t st);
+int launch_fuse_pyramid(const float* x3, const float* x4, const float* x5, float* out, __half* out_split, int B, int H3,
+                        int W3, cudaStream_t st);
 int launch_reliability(const xfeat_ctx* ctx, const float* t, float* out, int64_t npix, cudaStream_t st);
 int launch_kpt_softmax(const xfeat_ctx* ctx, const float* t, float* heat, float* logits, int B, int Hc, int Wc,
                        cudaStream_t st);

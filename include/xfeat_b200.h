@@ -79,6 +79,10 @@ XF_API int xfeat_preprocess(const void* d_img, int dtype, int B, int C, int Hi, 
                      int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255,
                      int H, int W, float* d_xn, double* d_stats, void* stream);
 
+/* Implementation switch of the 64->64 stride-1 conv layers inside xfeat_net (process-wide): 0 = fp32 CUDA-core kernels,
+ * 1 = tcgen05 tensor-core kernel (split-fp16 operands, fp32 accumulation in TMEM). */
+XF_API void xfeat_set_conv_impl(int impl);
+XF_API int xfeat_get_conv_impl(void);
 XF_API size_t xfeat_net_workspace_bytes(int B, int H, int W);
 /* replaces: XFeatModel.forward (model.py:123-154) minus the normalisation (done by xfeat_preprocess), plus
  * get_kpts_heatmap (xfeat.py:242-247) fused after keypoint_head.
@@ -150,6 +154,10 @@ XF_API int xfeat_refine(xfeat_ctx* ctx, const float* d_desc0, const float* d_des
  * kernels. in (B,Hi,Wi,Cin) NHWC -> out (B,Ho,Wo,Cout). */
 XF_API int xfeat_debug_conv_layer(xfeat_ctx* ctx, int layer, const float* d_in, int B, int Hi, int Wi, float* d_out,
                            void* stream);
+
+/* Test hook: one 64->64 stride-1 layer through the tensor-core kernel, fp32 NHWC in/out; d_scratch >= B*H*W*256 bytes. */
+XF_API int xfeat_debug_conv_layer_tc(xfeat_ctx* ctx, int layer, const float* d_in, int B, int H, int W, float* d_out,
+                                     void* d_scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

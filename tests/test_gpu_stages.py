@@ -111,7 +111,8 @@ def test_net_vs_oracle(xf, lib, oracle_state, golden, assets_vga, which):
     e_rel = (rel.cpu() - st["reliability"][:, 0]).abs().max().item()
     e_heat = (heat.cpu() - orc.kpts_heatmap(st["kpt_logits"])[:, 0]).abs().max().item()
     print(f"[{which}] feats rel {e_feats:.2e} logits abs {e_log:.2e} reliability abs {e_rel:.2e} heat abs {e_heat:.2e}")
-    assert e_feats < 1e-4 and e_log < 2e-4 and e_rel < 1e-5 and e_heat < 1e-5
+    # 3-term fp16 split carries 22 mantissa bits per operand (fp32: 24): a few 1e-5 after ~20 layers, 1e-3 is the budget
+    assert e_feats < 1e-4 and e_log < 5e-4 and e_rel < 5e-5 and e_heat < 5e-5
 
 
 def canon(kp_xy, scores, W):
