@@ -31,9 +31,9 @@ static void carve_net(Bump& bump, int B, int H, int W, NetWs& ws) {
   ws.a1 = bump.take<float>(p1 * 4);
   ws.a2 = bump.take<float>(p2 * 8);
   ws.a3 = bump.take<float>(p2 * 8);
-  ws.x1s = bump.take<float>(p4 * 24);
-  ws.t4a = bump.take<float>(p4 * 24);
-  ws.x2 = bump.take<float>(p4 * 24);
+  ws.x1s = bump.take<float>(p4 * 32);   // 24 fp32 channels, or split fp16 [hi(32) | lo(32)] = 128 B per pixel
+  ws.t4a = bump.take<float>(p4 * 32);
+  ws.x2 = bump.take<float>(p4 * 32);
   ws.t8a = bump.take<float>(p8 * 64);
   ws.t8b = bump.take<float>(p8 * 64);
   ws.x3 = bump.take<float>(p8 * 64);
@@ -132,31 +132,35 @@ extern "C" int xfeat_net(xfeat_ctx* ctx, const float* d_xn, int B, int H, int W,
   int rc;
 #define XF_RUN(call) \
   if ((rc = (call)) != XF_OK) return rc
-  // block1 + skip1 -> x1 + skip1(x)                                              model.py:139-140
-  XF_RUN(launch_stem_chain(ctx->h_weights, ctx->table, d_xn, ws.a1, ws.a2, ws.a3, ws.x1s, B, H, W, st));
-  // block2                                                                       model.py:140
-  XF_RUN(launch_conv_layer(ctx, L_B2_0, ws.x1s, IN_NHWC, B, H4, W4, ws.t4a, st));
-  XF_RUN(launch_conv_layer(ctx, L_B2_1, ws.t4a, IN_NHWC, B, H4, W4, ws.x2, st));
   if (g_conv_impl == 0) {
     // ------------------------------ all layers on the fp32 CUDA-core kernels ------------------------------
-    XF_RUN(launch_conv_layer(ctx, L_B3_0, ws.x2, IN_NHWC, B, H4, W4, ws.t8a, st));
+    // block1 + skip1 -> x1 + skip1(x)                                            model.py:139-140
+    XF_RUN(launch_stem_chain(ctx->h_weights, ctx->table, d_xn, ws.a1, ws.a2, ws.a3, ws.x1s, nullptr, B, H, W, st));
+    XF_RUN(launch_conv_layer(ctx, L_B2_0, ws.x1s, IN_NHWC, B, H4, W4, ws.t4a, st));                  // block2, model.py:140
+    XF_RUN(launch_conv_layer(ctx, L_B2_1, ws.t4a, IN_NHWC, B, H4, W4, ws.x2, st));
+    XF_RUN(launch_conv_layer(ctx, L_B3_0, ws.x2, IN_NHWC, B, H4, W4, ws.t8a, st));                   // block3, model.py:141
     XF_RUN(launch_conv_layer(ctx, L_B3_1, ws.t8a, IN_NHWC, B, H8, W8, ws.t8b, st));
     XF_RUN(launch_conv_layer(ctx, L_B3_2, ws.t8b, IN_NHWC, B, H8, W8, ws.x3, st));
-    XF_RUN(launch_conv_layer(ctx, L_B4_0, ws.x3, IN_NHWC, B, H8, W8, ws.t16a, st));
+    XF_RUN(launch_conv_layer(ctx, L_B4_0, ws.x3, IN_NHWC, B, H8, W8, ws.t16a, st));                  // block4, model.py:142
     XF_RUN(launch_conv_layer(ctx, L_B4_1, ws.t16a, IN_NHWC, B, H16, W16, ws.t16b, st));
     XF_RUN(launch_conv_layer(ctx, L_B4_2, ws.t16b, IN_NHWC, B, H16, W16, ws.x4, st));
+    XF_RUN(launch_conv_layer(ctx, L_B5_0, ws.x4, IN_NHWC, B, H16, W16, ws.t32a, st));                // block5, model.py:143
   } else {
-    // ------------- 64->64 stride-1 layers on tcgen05; activations between them travel as split fp16 -------------
+    // ---- block2 .. block5.0 on tcgen05; activations between tensor-core layers travel as split fp16 [hi | lo] ----
+    __half *s4a = (__half*)ws.x1s, *s4b = (__half*)ws.t4a, *s4c = (__half*)ws.x2;
     __half *s8a = (__half*)ws.t8a, *s8b = (__half*)ws.t8b, *s16a = (__half*)ws.t16a, *s16b = (__half*)ws.t16b;
-    XF_RUN(launch_conv_layer(ctx, L_B3_0, ws.x2, IN_NHWC, B, H4, W4, nullptr, st, nullptr, s8a));   // block3, model.py:141
+    XF_RUN(launch_stem_chain(ctx->h_weights, ctx->table, d_xn, ws.a1, ws.a2, ws.a3, nullptr, s4a, B, H, W, st));
+    XF_RUN(launch_conv_tc(ctx, L_B2_0, s4a, B, H4, W4, s4b, nullptr, st));                           // block2, model.py:140
+    XF_RUN(launch_conv_tc(ctx, L_B2_1, s4b, B, H4, W4, s4c, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_B3_0, s4c, B, H4, W4, s8a, nullptr, st));                           // block3 (stride 2), model.py:141
     XF_RUN(launch_conv_tc(ctx, L_B3_1, s8a, B, H8, W8, s8b, nullptr, st));
-    XF_RUN(launch_conv_tc(ctx, L_B3_2, s8b, B, H8, W8, nullptr, ws.x3, st));
-    XF_RUN(launch_conv_layer(ctx, L_B4_0, ws.x3, IN_NHWC, B, H8, W8, nullptr, st, nullptr, s16a));  // block4, model.py:142
+    XF_RUN(launch_conv_tc(ctx, L_B3_2, s8b, B, H8, W8, s8a, ws.x3, st));       // x3: fp32 for the fusion, split for block4.0
+    XF_RUN(launch_conv_tc(ctx, L_B4_0, s8a, B, H8, W8, s16a, nullptr, st));                          // block4 (stride 2), model.py:142
     XF_RUN(launch_conv_tc(ctx, L_B4_1, s16a, B, H16, W16, s16b, nullptr, st));
-    XF_RUN(launch_conv_tc(ctx, L_B4_2, s16b, B, H16, W16, nullptr, ws.x4, st));
+    XF_RUN(launch_conv_tc(ctx, L_B4_2, s16b, B, H16, W16, s16a, ws.x4, st));   // x4: fp32 for the fusion, split for block5.0
+    XF_RUN(launch_conv_tc(ctx, L_B5_0, s16a, B, H16, W16, nullptr, ws.t32a, st));                    // block5 (stride 2), model.py:143
   }
-  // block5                                                                       model.py:143
-  XF_RUN(launch_conv_layer(ctx, L_B5_0, ws.x4, IN_NHWC, B, H16, W16, ws.t32a, st));
+  // rest of block5 (128 channels: fp32 CUDA-core kernel)                         model.py:143
   XF_RUN(launch_conv_layer(ctx, L_B5_1, ws.t32a, IN_NHWC, B, H32, W32, ws.t32b, st));
   XF_RUN(launch_conv_layer(ctx, L_B5_2, ws.t32b, IN_NHWC, B, H32, W32, ws.t32a, st));
   XF_RUN(launch_conv_layer(ctx, L_B5_3, ws.t32a, IN_NHWC, B, H32, W32, ws.x5, st));

@@ -25,33 +25,48 @@
 namespace xf {
 
 constexpr int CT_THREADS = 192;
-constexpr int CT_ABOX = 128 * 128;   // bytes: 128 pixels x 64 halves
-constexpr int CT_WBOX = 64 * 128;    // bytes: 64 cout x 64 halves
+constexpr int CT_ABOX = 128 * 128;   // bytes: 128 pixels x 128 B (64 halves)
 
-template <int KS>
+// CINP = padded input channels per term (64: two boxes per tap, hi and lo; 32: ONE box per tap whose 128-byte rows are
+// [hi(32) | lo(32)]).  NOUT = output channels of this CTA's N tile (32 or 64).  Weight rows are 64 halves (128 B):
+//   CINP = 64: group 0 = whi, group 1 = wlo                          -> hi.whi, hi.wlo, lo.whi  (3 x 4 K-steps)
+//   CINP = 32: group 0 = [whi | whi], group 1 = [wlo | 0]            -> [hi|lo].[whi|whi] (4 K-steps) + hi.wlo (2 K-steps)
+template <int KS, int CINP, int NOUT>
 struct ConvTcCfg {
   static constexpr int TAPS = KS * KS;
-  static constexpr int NS = (KS == 3) ? 2 : 4;                       // A stages (one tap = hi + lo box each)
-  static constexpr size_t W_BYTES = (size_t)TAPS * 2 * CT_WBOX;
-  static constexpr size_t A_BYTES = (size_t)NS * 2 * CT_ABOX;
-  static constexpr size_t SMEM = 1024 + W_BYTES + A_BYTES + 512;
+  static constexpr int A_BOXES = CINP / 32;                           // 1 or 2
+  static constexpr int A_STAGE = A_BOXES * CT_ABOX;
+  static constexpr int W_GROUP = NOUT * 128;                          // bytes
+  static constexpr size_t W_BYTES = (size_t)TAPS * 2 * W_GROUP;
+  static constexpr int NS_MAX = (int)((227 * 1024 - 2048 - W_BYTES) / A_STAGE);
+  static constexpr int NS = NS_MAX > 6 ? 6 : NS_MAX;                  // A stages (one tap each)
+  static constexpr size_t A_BYTES = (size_t)NS * A_STAGE;
+  static constexpr size_t SMEM = 1024 + W_BYTES + A_BYTES + 768;
+  static constexpr int TMEM_COLS = 2 * NOUT < 32 ? 32 : 2 * NOUT;     // two accumulator buffers (power of two >= 32)
+  static_assert(NS >= 2, "need at least two A stages");
+  static_assert(CINP == 32 || CINP == 64, "CINP");
+  static_assert(NOUT == 32 || NOUT == 64, "NOUT");
 };
 
 struct ConvTcParams {
-  CUtensorMap amap;   // input activations, split fp16 (B,H,W,128)
-  CUtensorMap wmap;   // weights [tap][term][cout][cin] fp16
-  const float* bias;
+  CUtensorMap amap;   // input activations, split fp16 (B,Hin,Win,2*CINP); box {64, S*TW, S*TH, 1}, element strides {1,S,S,1}
+  CUtensorMap wmap;   // weights of this N tile: rows [tap][group][NOUT] x 64 halves
+  const float* bias;  // bias + co0
   float inv_wscale;
-  int B, H, W;
+  int B, H, W;        // OUTPUT height / width
+  int stride;         // 1 or 2
+  int pad;            // KS / 2
   int tw_log2;        // TW = 1 << tw_log2, TH = 128 / TW
-  __half* out_split;  // (B,H,W,128) or null
-  float* out_f32;     // (B,H,W,64) or null
+  __half* out_split;  // (B,H,W,2*split_c) [hi(split_c) | lo(split_c)] or null; split_c = 32 or 64
+  int split_c;
+  float* out_f32;     // (B,H,W,f32_c) or null; this CTA's channels start at f32_co0, n_real of them are real
+  int f32_c, f32_co0, n_real;
   int relu;
 };
 
-template <int KS>
+template <int KS, int CINP, int NOUT>
 __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
-  using C = ConvTcCfg<KS>;
+  using C = ConvTcCfg<KS, CINP, NOUT>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sW = base;
@@ -71,7 +86,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   const int tiles_img = tiles_x * tiles_y;
   const int n_tiles = tiles_img * P.B;
 
-  if (threadIdx.x < 64) sBias[threadIdx.x] = __ldg(P.bias + threadIdx.x);
+  if (threadIdx.x < NOUT) sBias[threadIdx.x] = (threadIdx.x < P.n_real) ? __ldg(P.bias + threadIdx.x) : 0.f;
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&P.amap);
     tc::tma_prefetch_desc(&P.wmap);
@@ -87,7 +102,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     tc::fence_barrier_init();
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 128);
+    tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc::tmem_relinquish();
   }
   tc::tc_fence_before();
@@ -99,20 +114,20 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       tc::mbar_expect_tx(w_full, (uint32_t)C::W_BYTES);
-      for (int i = 0; i < C::TAPS * 2; ++i) tc::tma_load_2d(sW + i * CT_WBOX, &P.wmap, w_full, 0, i * 64);
+      for (int i = 0; i < C::TAPS * 2; ++i) tc::tma_load_2d(sW + (size_t)i * C::W_GROUP, &P.wmap, w_full, 0, i * NOUT);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int b = tile / tiles_img, rem = tile - b * tiles_img;
-        const int y0 = (rem / tiles_x) * TH, x0 = (rem % tiles_x) * TW;
+        const int y0 = (rem / tiles_x) * TH * P.stride - P.pad, x0 = (rem % tiles_x) * TW * P.stride - P.pad;
         for (int tap = 0; tap < C::TAPS; ++tap, ++it) {
           const int s = it % C::NS;
           const uint32_t ph = (it / C::NS) & 1;
-          const int dy = (KS == 3) ? tap / 3 - 1 : 0, dx = (KS == 3) ? tap % 3 - 1 : 0;
+          const int dy = (KS == 3) ? tap / 3 : 0, dx = (KS == 3) ? tap % 3 : 0;
           tc::mbar_wait(&a_empty[s], ph ^ 1);
-          tc::mbar_expect_tx(&a_full[s], 2 * CT_ABOX);
-          unsigned char* dst = sA + (size_t)s * 2 * CT_ABOX;
-          tc::tma_load_4d(dst, &P.amap, &a_full[s], 0, x0 + dx, y0 + dy, b);               // hi half of the channels
-          tc::tma_load_4d(dst + CT_ABOX, &P.amap, &a_full[s], 64, x0 + dx, y0 + dy, b);    // lo half
+          tc::mbar_expect_tx(&a_full[s], C::A_STAGE);
+          unsigned char* dst = sA + (size_t)s * C::A_STAGE;
+          tc::tma_load_4d(dst, &P.amap, &a_full[s], 0, x0 + dx, y0 + dy, b);                    // hi (CINP=64) or [hi|lo]
+          if (C::A_BOXES == 2) tc::tma_load_4d(dst + CT_ABOX, &P.amap, &a_full[s], 64, x0 + dx, y0 + dy, b);  // lo
         }
       }
     }
@@ -120,28 +135,36 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, 64);
+      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);
       tc::mbar_wait(w_full, 0);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         const int a = tcount & 1;
         tc::mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
         tc::tc_fence_after();
-        const uint32_t d = tmem + a * 64;
+        const uint32_t d = tmem + a * NOUT;
         for (int tap = 0; tap < C::TAPS; ++tap, ++it) {
           const int s = it % C::NS;
           tc::mbar_wait(&a_full[s], (it / C::NS) & 1);
           tc::tc_fence_after();
-          const uint32_t a_addr = tc::smem_u32(sA + (size_t)s * 2 * CT_ABOX);
-          const uint32_t w_addr = tc::smem_u32(sW + (size_t)tap * 2 * CT_WBOX);
-          const uint64_t ahi = tc::make_desc_sw128(a_addr, 1024), alo = tc::make_desc_sw128(a_addr + CT_ABOX, 1024);
-          const uint64_t whi = tc::make_desc_sw128(w_addr, 1024), wlo = tc::make_desc_sw128(w_addr + CT_WBOX, 1024);
+          const uint32_t a_addr = tc::smem_u32(sA + (size_t)s * C::A_STAGE);
+          const uint32_t w_addr = tc::smem_u32(sW + (size_t)tap * 2 * C::W_GROUP);
+          const uint64_t a0 = tc::make_desc_sw128(a_addr, 1024);
+          const uint64_t w0 = tc::make_desc_sw128(w_addr, 1024), w1 = tc::make_desc_sw128(w_addr + C::W_GROUP, 1024);
+          if (C::A_BOXES == 2) {
+            const uint64_t a1 = tc::make_desc_sw128(a_addr + CT_ABOX, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, whi + 2 * k, idesc, (tap | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc, (tap | k) ? 1u : 0u);   // hi . whi
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w1 + 2 * k, idesc, 1u);                    // hi . wlo
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::umma_f16(d, alo + 2 * k, whi + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a1 + 2 * k, w0 + 2 * k, idesc, 1u);                    // lo . whi
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc, (tap | k) ? 1u : 0u);   // [hi|lo].[whi|whi]
+#pragma unroll
+            for (int k = 0; k < 2; ++k) tc::umma_f16(d, a0 + 2 * k, w1 + 2 * k, idesc, 1u);                    // hi . wlo
+          }
           tc::umma_commit(&a_empty[s]);
         }
         tc::umma_commit(&acc_full[a]);
@@ -160,33 +183,39 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
       const int y = (rem / tiles_x) * TH + ph_, x = (rem % tiles_x) * TW + pw_;
       tc::mbar_wait(&acc_full[a], (tcount >> 1) & 1);
       tc::tc_fence_after();
-      uint32_t v0[32], v1[32];
+      uint32_t v[NOUT];
       __syncwarp();
-      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * 64, v0);
-      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * 64 + 32, v1);
+#pragma unroll
+      for (int c = 0; c < NOUT / 32; ++c) {
+        uint32_t t[32];
+        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * NOUT + c * 32, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[c * 32 + j] = t[j];
+      }
       tc::tmem_ld_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[a]);   // TMEM buffer is free again: the stores below overlap the next MMAs
       if (y < P.H && x < P.W) {
         const int64_t pix = ((int64_t)b * P.H + y) * P.W + x;
-        float o[64];
+        float o[NOUT];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          float t0 = fmaf(__uint_as_float(v0[c]), P.inv_wscale, sBias[c]);
-          float t1 = fmaf(__uint_as_float(v1[c]), P.inv_wscale, sBias[32 + c]);
-          if (P.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
-          o[c] = t0; o[32 + c] = t1;
+        for (int c = 0; c < NOUT; ++c) {
+          float t0 = fmaf(__uint_as_float(v[c]), P.inv_wscale, sBias[c]);
+          if (P.relu) t0 = fmaxf(t0, 0.f);
+          o[c] = t0;
         }
         if (P.out_f32) {
-          float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * 64);
+          float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * P.f32_c + P.f32_co0);
 #pragma unroll
-          for (int c = 0; c < 16; ++c) op[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+          for (int c = 0; c < NOUT / 4; ++c)
+            if (4 * c < P.n_real) op[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
         }
         if (P.out_split) {
-          uint4* hp = reinterpret_cast<uint4*>(P.out_split + pix * 128);
+          // [hi(split_c) | lo(split_c)]; this kernel only produces split_c == NOUT (padded channels are exact zeros)
+          uint4* hp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * NOUT));
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < NOUT / 8; ++c) {
             __half2 h[4], l[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -197,8 +226,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             }
             hp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
                                *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
-            hp[8 + c] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
-                                   *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
+            hp[NOUT / 8 + c] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                                          *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
           }
         }
       }
@@ -208,7 +237,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem, 128);
+    tc::tmem_dealloc(tmem, C::TMEM_COLS);
   }
 }
 
@@ -229,19 +258,24 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
                   *reinterpret_cast<uint32_t*>(&l[3]));
 }
 
-__global__ void __launch_bounds__(256) split_nhwc64_kernel(const float* __restrict__ in, __half* __restrict__ out,
-                                                           int64_t npix) {
+// fp32 NHWC with C real channels (multiple of 8) -> split fp16 NHWC [hi(CP) | lo(CP)], channels C..CP-1 zero.
+__global__ void __launch_bounds__(256) split_nhwc_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t npix,
+                                                         int C, int CP) {
+  const int G = CP / 8;
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (pixel, 8-channel group)
-  if (gid >= npix * 8) return;
-  const int64_t pix = gid >> 3;
-  const int g = (int)(gid & 7);
-  const float4 a = __ldg(reinterpret_cast<const float4*>(in + pix * 64) + 2 * g);
-  const float4 b = __ldg(reinterpret_cast<const float4*>(in + pix * 64) + 2 * g + 1);
-  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (gid >= npix * G) return;
+  const int64_t pix = gid / G;
+  const int g = (int)(gid - pix * G);
+  float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (8 * g < C) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in + pix * C) + 2 * g);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(in + pix * C) + 2 * g + 1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+  }
   uint4 hi, lo;
   split8(x, hi, lo);
-  reinterpret_cast<uint4*>(out + pix * 128)[g] = hi;
-  reinterpret_cast<uint4*>(out + pix * 128)[8 + g] = lo;
+  reinterpret_cast<uint4*>(out + pix * 2 * CP)[g] = hi;
+  reinterpret_cast<uint4*>(out + pix * 2 * CP)[G + g] = lo;
 }
 
 // XFeatModel._unfold2d(x, 8) (model.py:113-120) fused with the split: channel 8i+j of cell (h,w) = xn[8h+i, 8w+j].
@@ -263,8 +297,8 @@ __global__ void __launch_bounds__(256) unfold8_split_kernel(const float* __restr
   reinterpret_cast<uint4*>(out + cell * 128)[8 + i] = lo;
 }
 
-int launch_split_nhwc64(const float* in, __half* out, int64_t npix, cudaStream_t st) {
-  split_nhwc64_kernel<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, st>>>(in, out, npix);
+int launch_split_nhwc(const float* in, __half* out, int64_t npix, int C, int CP, cudaStream_t st) {
+  split_nhwc_kernel<<<(unsigned)((npix * (CP / 8) + 255) / 256), 256, 0, st>>>(in, out, npix, C, CP);
   XF_LAUNCH_CHECK();
   return XF_OK;
 }
@@ -278,65 +312,66 @@ int launch_unfold8_split(const float* xn, __half* out, int B, int Hc, int Wc, cu
 // ---------------------------------------------------------------------------------------------------------------------
 // host: weight preparation at context creation, per-launch tensor maps
 // ---------------------------------------------------------------------------------------------------------------------
-bool conv_tc_eligible(int layer) {
+// Layers that run on the tensor-core kernel and their operand geometry.
+struct TcLayer { int cinp, nout, ntiles; };
+static bool tc_layer_cfg(int layer, TcLayer& c) {
+  if (layer >= L_FM_0) return false;
   const LayerSpec& s = kLayers[layer];
-  return layer < L_FM_0 && s.cin == 64 && s.cout == 64 && s.stride == 1;
+  if (s.cin == 64 && s.cout == 64) { c = {64, 64, 1}; return true; }            // block3.1/2, block4.*, fusion, heads
+  if (s.cin == 24 && s.cout == 24) { c = {32, 32, 1}; return true; }            // block2 (channels padded 24 -> 32)
+  if (s.cin == 24 && s.cout == 64) { c = {32, 64, 1}; return true; }            // block3.0 (stride 2)
+  if (s.cin == 64 && s.cout == 128) { c = {64, 64, 2}; return true; }           // block5.0 (stride 2), two N tiles
+  return false;
+}
+bool conv_tc_eligible(int layer) {
+  TcLayer c;
+  return tc_layer_cfg(layer, c);
 }
 
 int conv_tc_prepare(xfeat_ctx* ctx) {
-  // split weights: W[tap][cin][cout] fp32 (BN folded) -> [tap][term][cout][cin] fp16 of W * 2^k
+  // split weights: W[tap][cin][cout] fp32 (BN folded) * 2^k -> per N tile rows [tap][group][NOUT] x 64 halves
   size_t total = 0;
   for (int l = 0; l < L_COUNT; ++l) {
     ctx->tc_off[l] = (size_t)-1;
-    if (conv_tc_eligible(l)) {
+    TcLayer c;
+    if (tc_layer_cfg(l, c)) {
       ctx->tc_off[l] = total;
-      total += (size_t)kLayers[l].ks * kLayers[l].ks * 2 * 64 * 64;
+      total += (size_t)c.ntiles * kLayers[l].ks * kLayers[l].ks * 2 * c.nout * 64;
     }
   }
-  std::vector<__half> h(total);
+  std::vector<__half> h(total, __float2half_rn(0.f));
   for (int l = 0; l < L_COUNT; ++l) {
-    if (ctx->tc_off[l] == (size_t)-1) continue;
-    const int taps = kLayers[l].ks * kLayers[l].ks;
+    TcLayer c;
+    if (!tc_layer_cfg(l, c)) continue;
+    const LayerSpec& sp = kLayers[l];
+    const int taps = sp.ks * sp.ks;
     const float* w = ctx->h_weights + ctx->table.w_off[l];
     float mx = 0.f;
-    for (int i = 0; i < taps * 64 * 64; ++i) mx = fmaxf(mx, fabsf(w[i]));
+    for (int i = 0; i < taps * sp.cin * sp.cout; ++i) mx = fmaxf(mx, fabsf(w[i]));
     int e = 0;
     if (mx > 0.f) frexpf(mx, &e);
     const float s = (mx > 0.f) ? ldexpf(1.f, 13 - e) : 1.f;          // max|w| * s in [2^12, 2^13)
     ctx->tc_inv_wscale[l] = (mx > 0.f) ? ldexpf(1.f, e - 13) : 1.f;
-    __half* dst = h.data() + ctx->tc_off[l];
-    for (int t = 0; t < taps; ++t)
-      for (int co = 0; co < 64; ++co)
-        for (int ci = 0; ci < 64; ++ci) {
-          const float v = w[((size_t)t * 64 + ci) * 64 + co] * s;
-          const __half hi = __float2half_rn(v);
-          const __half lo = __float2half_rn(v - __half2float(hi));
-          dst[(((size_t)t * 2 + 0) * 64 + co) * 64 + ci] = hi;
-          dst[(((size_t)t * 2 + 1) * 64 + co) * 64 + ci] = lo;
+    for (int nt = 0; nt < c.ntiles; ++nt) {
+      __half* dst = h.data() + ctx->tc_off[l] + (size_t)nt * taps * 2 * c.nout * 64;
+      for (int t = 0; t < taps; ++t)
+        for (int n = 0; n < c.nout; ++n) {
+          const int co = nt * c.nout + n;
+          __half* g0 = dst + (((size_t)t * 2 + 0) * c.nout + n) * 64;
+          __half* g1 = dst + (((size_t)t * 2 + 1) * c.nout + n) * 64;
+          if (co >= sp.cout) continue;                                 // padded output channel: zero row
+          for (int ci = 0; ci < sp.cin; ++ci) {
+            const float v = w[((size_t)t * sp.cin + ci) * sp.cout + co] * s;
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            if (c.cinp == 64) { g0[ci] = hi; g1[ci] = lo; }
+            else { g0[ci] = hi; g0[32 + ci] = hi; g1[ci] = lo; }      // [whi|whi], [wlo|0]
+          }
         }
+    }
   }
   XF_CUDA(cudaMalloc(&ctx->d_tcw, total * sizeof(__half)));
   XF_CUDA(cudaMemcpy(ctx->d_tcw, h.data(), total * sizeof(__half), cudaMemcpyHostToDevice));
-  PFN_encodeTiled enc = get_encode_tiled();
-  if (!enc) {
-    set_error("cuTensorMapEncodeTiled entry point not available");
-    return XF_E_CUDA;
-  }
-  for (int l = 0; l < L_COUNT; ++l) {
-    if (ctx->tc_off[l] == (size_t)-1) continue;
-    const int taps = kLayers[l].ks * kLayers[l].ks;
-    const cuuint64_t dims[2] = {64, (cuuint64_t)taps * 2 * 64};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {64, 64};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&ctx->tc_wmap[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)((__half*)ctx->d_tcw + ctx->tc_off[l]), dims,
-                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled(weights, layer %d) failed: %d", l, (int)r);
-      return XF_E_CUDA;
-    }
-  }
   return XF_OK;
 }
 
@@ -352,53 +387,88 @@ static void pick_tile(int H, int W, int& tw_log2) {
   tw_log2 = best;
 }
 
-// in_split: (B,H,W,128) halves. Any of out_split / out_f32 may be null (not both).
-int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int H, int W, __half* out_split,
+template <int KS, int CINP, int NOUT>
+static int launch_tc_cfg(const ConvTcParams& P, int grid, cudaStream_t st) {
+  using C = ConvTcCfg<KS, CINP, NOUT>;
+  static bool attr = false;
+  if (!attr) {
+    XF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, CINP, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    attr = true;
+  }
+  conv_tc_kernel<KS, CINP, NOUT><<<grid, CT_THREADS, C::SMEM, st>>>(P);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+// in_split: (B,Hin,Win,2*CINP) halves [hi|lo].  out_split (optional): (B,Ho,Wo,2*NOUT); out_f32 (optional): (B,Ho,Wo,cout).
+int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int Hin, int Win, __half* out_split,
                    float* out_f32, cudaStream_t st) {
-  XF_REQUIRE(conv_tc_eligible(layer) && ctx->d_tcw, "conv_tc: layer %d not prepared for the tensor-core path", layer);
+  TcLayer c;
+  XF_REQUIRE(tc_layer_cfg(layer, c) && ctx->d_tcw, "conv_tc: layer %d not prepared for the tensor-core path", layer);
   XF_REQUIRE(out_split || out_f32, "conv_tc: no output");
+  XF_REQUIRE(!(out_split && c.ntiles > 1), "conv_tc: split output needs a single N tile");
   PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return XF_E_CUDA;
+  }
+  const LayerSpec& sp = kLayers[layer];
+  const int S = sp.stride, Ho = Hin / S, Wo = Win / S;
   ConvTcParams P;
   int tw_log2;
-  pick_tile(H, W, tw_log2);
+  pick_tile(Ho, Wo, tw_log2);
   const int TW = 1 << tw_log2, TH = 128 >> tw_log2;
-  const cuuint64_t dims[4] = {128, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  const cuuint64_t strides[3] = {256, (cuuint64_t)W * 256, (cuuint64_t)H * W * 256};
-  const cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint64_t row_bytes = (cuuint64_t)2 * c.cinp * sizeof(__half);
+  const cuuint64_t dims[4] = {(cuuint64_t)2 * c.cinp, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {row_bytes, (cuuint64_t)Win * row_bytes, (cuuint64_t)Hin * Win * row_bytes};
+  const cuuint32_t box[4] = {64, (cuuint32_t)(TW * S), (cuuint32_t)(TH * S), 1};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)S, (cuuint32_t)S, 1};
   CUresult r = enc(&P.amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)in_split, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(activations %dx%dx%d) failed: %d", B, H, W, (int)r);
+    set_error("cuTensorMapEncodeTiled(activations %dx%dx%d, stride %d) failed: %d", B, Hin, Win, S, (int)r);
     return XF_E_CUDA;
   }
-  P.wmap = ctx->tc_wmap[layer];
-  P.bias = ctx->d_weights + ctx->table.b_off[layer];
+  const int taps = sp.ks * sp.ks;
   P.inv_wscale = ctx->tc_inv_wscale[layer];
-  P.B = B; P.H = H; P.W = W;
+  P.B = B; P.H = Ho; P.W = Wo;
+  P.stride = S;
+  P.pad = sp.ks / 2;
   P.tw_log2 = tw_log2;
   P.out_split = out_split;
+  P.split_c = c.nout;
   P.out_f32 = out_f32;
-  P.relu = kLayers[layer].relu;
-  const int n_tiles = cdiv(H, TH) * cdiv(W, TW) * B;
+  P.f32_c = sp.cout;
+  P.relu = sp.relu;
+  const int n_tiles = cdiv(Ho, TH) * cdiv(Wo, TW) * B;
   const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
-  if (kLayers[layer].ks == 3) {
-    static bool attr3 = false;
-    if (!attr3) {
-      XF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvTcCfg<3>::SMEM));
-      attr3 = true;
+  for (int nt = 0; nt < c.ntiles; ++nt) {
+    const cuuint64_t wdims[2] = {64, (cuuint64_t)taps * 2 * c.nout};
+    const cuuint64_t wstrides[1] = {128};
+    const cuuint32_t wbox[2] = {64, (cuuint32_t)c.nout};
+    const cuuint32_t westr[2] = {1, 1};
+    __half* wptr = (__half*)ctx->d_tcw + ctx->tc_off[layer] + (size_t)nt * taps * 2 * c.nout * 64;
+    r = enc(&P.wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)wptr, wdims, wstrides, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(weights, layer %d) failed: %d", layer, (int)r);
+      return XF_E_CUDA;
     }
-    conv_tc_kernel<3><<<grid, CT_THREADS, ConvTcCfg<3>::SMEM, st>>>(P);
-  } else {
-    static bool attr1 = false;
-    if (!attr1) {
-      XF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvTcCfg<1>::SMEM));
-      attr1 = true;
+    P.bias = ctx->d_weights + ctx->table.b_off[layer] + nt * c.nout;
+    P.f32_co0 = nt * c.nout;
+    P.n_real = sp.cout - nt * c.nout < c.nout ? sp.cout - nt * c.nout : c.nout;
+    int rc;
+    if (sp.ks == 3 && c.cinp == 64 && c.nout == 64) rc = launch_tc_cfg<3, 64, 64>(P, grid, st);
+    else if (sp.ks == 1 && c.cinp == 64 && c.nout == 64) rc = launch_tc_cfg<1, 64, 64>(P, grid, st);
+    else if (sp.ks == 3 && c.cinp == 32 && c.nout == 32) rc = launch_tc_cfg<3, 32, 32>(P, grid, st);
+    else if (sp.ks == 3 && c.cinp == 32 && c.nout == 64) rc = launch_tc_cfg<3, 32, 64>(P, grid, st);
+    else {
+      set_error("conv_tc: no kernel instantiation for layer %d", layer);
+      return XF_E_UNSUPPORTED;
     }
-    conv_tc_kernel<1><<<grid, CT_THREADS, ConvTcCfg<1>::SMEM, st>>>(P);
+    if (rc) return rc;
   }
-  XF_LAUNCH_CHECK();
   return XF_OK;
 }
 
@@ -408,11 +478,13 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
 extern "C" int xfeat_debug_conv_layer_tc(xfeat_ctx* ctx, int layer, const float* d_in, int B, int H, int W, float* d_out,
                                          void* d_scratch, size_t scratch_bytes, void* stream) {
   XF_REQUIRE(ctx && d_in && d_out && d_scratch && layer >= 0 && layer < xf::L_COUNT, "debug_conv_layer_tc: bad arguments");
+  XF_REQUIRE(xf::conv_tc_eligible(layer), "debug_conv_layer_tc: layer %d has no tensor-core configuration", layer);
+  const int cin = xf::kLayers[layer].cin, cinp = cin <= 32 ? 32 : 64;
   const int64_t npix = (int64_t)B * H * W;
-  XF_REQUIRE(scratch_bytes >= (size_t)npix * 256, "debug_conv_layer_tc: scratch must hold B*H*W*256 bytes");
+  XF_REQUIRE(scratch_bytes >= (size_t)npix * 4 * cinp, "debug_conv_layer_tc: scratch must hold B*H*W*%d bytes", 4 * cinp);
   XF_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = xf::launch_split_nhwc64(d_in, (__half*)d_scratch, npix, st);
+  int rc = xf::launch_split_nhwc(d_in, (__half*)d_scratch, npix, cin, cinp, st);
   if (rc) return rc;
   return xf::launch_conv_tc(ctx, layer, (const __half*)d_scratch, B, H, W, nullptr, d_out, st);
 }

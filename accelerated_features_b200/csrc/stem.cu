@@ -35,7 +35,8 @@ template <int CIN, int COUT, int S, bool SKIP>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ StemW<CIN, COUT> P,
                                                         const __grid_constant__ SkipW K,
                                                         const float* __restrict__ in, const float* __restrict__ xn,
-                                                        float* __restrict__ out, int Hi, int Wi, int Ho, int Wo) {
+                                                        float* __restrict__ out, __half* __restrict__ out_split32, int Hi,
+                                                        int Wi, int Ho, int Wo) {
   const int ox = blockIdx.x * 32 + (threadIdx.x & 31);
   const int oy = blockIdx.y * 4 + (threadIdx.x >> 5);
   const int b = blockIdx.z;
@@ -77,24 +78,45 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
     }
     skipv = s * (1.0f / 16.0f);
   }
+  float res[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) {
+    float v = fmaxf(acc[co] + P.b[co], 0.f);
+    if constexpr (SKIP) v += fmaf(skipv, K.w[co], K.b[co]);
+    res[co] = v;
+  }
+  if constexpr (COUT == 24) {
+    if (out_split32 != nullptr) {
+      // feed the tensor-core block2: [hi(32) | lo(32)] fp16 per pixel, channels 24..31 zero (conv_tc.cu)
+      uint4* sp = reinterpret_cast<uint4*>(out_split32 + (((int64_t)b * Ho + oy) * Wo + ox) * 64);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 8 * g + 2 * j;
+          const float x0 = (c < 24) ? res[c < 24 ? c : 0] : 0.f, x1 = (c + 1 < 24) ? res[c + 1 < 24 ? c + 1 : 0] : 0.f;
+          const __half2 h = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+          hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+          lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        sp[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        sp[4 + g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      return;
+    }
+  }
   float* op = out + (((int64_t)b * Ho + oy) * Wo + ox) * COUT;
 #pragma unroll
-  for (int c4 = 0; c4 < COUT / 4; ++c4) {
-    float r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = 4 * c4 + j;
-      float v = fmaxf(acc[co] + P.b[co], 0.f);
-      if constexpr (SKIP) v += fmaf(skipv, K.w[co], K.b[co]);
-      r[j] = v;
-    }
-    reinterpret_cast<float4*>(op)[c4] = make_float4(r[0], r[1], r[2], r[3]);
-  }
+  for (int c4 = 0; c4 < COUT / 4; ++c4)
+    reinterpret_cast<float4*>(op)[c4] = make_float4(res[4 * c4], res[4 * c4 + 1], res[4 * c4 + 2], res[4 * c4 + 3]);
 }
 
 template <int CIN, int COUT, int S, bool SKIP>
 static int launch_stem(const float* hw, const float* hb, const float* sw, const float* sb, const float* in,
-                       const float* xn, float* out, int B, int Hi, int Wi, cudaStream_t st) {
+                       const float* xn, float* out, __half* out_split32, int B, int Hi, int Wi, cudaStream_t st) {
   StemW<CIN, COUT> P;
   memcpy(P.w, hw, sizeof(P.w));
   memcpy(P.b, hb, sizeof(P.b));
@@ -103,24 +125,24 @@ static int launch_stem(const float* hw, const float* hb, const float* sw, const 
   if (SKIP) { memcpy(K.w, sw, sizeof(K.w)); memcpy(K.b, sb, sizeof(K.b)); }
   const int Ho = Hi / S, Wo = Wi / S;
   dim3 grid(cdiv(Wo, 32), cdiv(Ho, 4), B);
-  stem_conv_kernel<CIN, COUT, S, SKIP><<<grid, 128, 0, st>>>(P, K, in, xn, out, Hi, Wi, Ho, Wo);
+  stem_conv_kernel<CIN, COUT, S, SKIP><<<grid, 128, 0, st>>>(P, K, in, xn, out, out_split32, Hi, Wi, Ho, Wo);
   XF_LAUNCH_CHECK();
   return XF_OK;
 }
 
 // xn (B,H,W) -> a1 (B,H,W,4) -> a2 (B,H/2,W/2,8) -> a3 (same,8) -> x1s (B,H/4,W/4,24) = block1(x) + skip1(x)
 int launch_stem_chain(const float* h_weights, const LayerTable& t, const float* xn, float* a1, float* a2, float* a3,
-                      float* x1s, int B, int H, int W, cudaStream_t st) {
+                      float* x1s, __half* x1s_split32, int B, int H, int W, cudaStream_t st) {
   const float* hw = h_weights;
   int rc;
-  rc = launch_stem<1, 4, 1, false>(hw + t.w_off[L_B1_0], hw + t.b_off[L_B1_0], nullptr, nullptr, xn, nullptr, a1, B, H, W, st);
+  rc = launch_stem<1, 4, 1, false>(hw + t.w_off[L_B1_0], hw + t.b_off[L_B1_0], nullptr, nullptr, xn, nullptr, a1, nullptr, B, H, W, st);
   if (rc) return rc;
-  rc = launch_stem<4, 8, 2, false>(hw + t.w_off[L_B1_1], hw + t.b_off[L_B1_1], nullptr, nullptr, a1, nullptr, a2, B, H, W, st);
+  rc = launch_stem<4, 8, 2, false>(hw + t.w_off[L_B1_1], hw + t.b_off[L_B1_1], nullptr, nullptr, a1, nullptr, a2, nullptr, B, H, W, st);
   if (rc) return rc;
-  rc = launch_stem<8, 8, 1, false>(hw + t.w_off[L_B1_2], hw + t.b_off[L_B1_2], nullptr, nullptr, a2, nullptr, a3, B, H / 2, W / 2, st);
+  rc = launch_stem<8, 8, 1, false>(hw + t.w_off[L_B1_2], hw + t.b_off[L_B1_2], nullptr, nullptr, a2, nullptr, a3, nullptr, B, H / 2, W / 2, st);
   if (rc) return rc;
   rc = launch_stem<8, 24, 2, true>(hw + t.w_off[L_B1_3], hw + t.b_off[L_B1_3], hw + t.w_off[L_SKIP1], hw + t.b_off[L_SKIP1],
-                                   a3, xn, x1s, B, H / 2, W / 2, st);
+                                   a3, xn, x1s, x1s_split32, B, H / 2, W / 2, st);
   return rc;
 }
 

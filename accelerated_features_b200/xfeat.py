@@ -112,12 +112,12 @@ class XFeat:
             x = x.float()          # same as the reference's `.float()` (xfeat.py:233)
         return x, 0
 
-    def _preprocess(self, x: torch.Tensor, H: int, W: int, div255: bool) -> torch.Tensor:
-        """xfeat_preprocess: resize to (H,W), channel mean, InstanceNorm -> (B,H,W) fp32."""
+    def _preprocess(self, x: torch.Tensor, H: int, W: int, div255: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """xfeat_preprocess: resize to (H,W), channel mean, InstanceNorm -> (B,H,W) fp32 (optionally into `out`)."""
         x, code = self._img_args(x)
         B, C, Hi, Wi = x.shape
         sb, sc, sh, sw = x.stride()
-        xn = self._empty((B, H, W))
+        xn = self._empty((B, H, W)) if out is None else out
         stats = self._empty((B, 2), torch.float64)
         with torch.cuda.device(self.dev):
             _lib.check(self._lib.xfeat_preprocess(x.data_ptr(), code, B, C, Hi, Wi, sb, sc, sh, sw, int(div255), H, W,
@@ -154,15 +154,23 @@ class XFeat:
     # sparse path
     # ------------------------------------------------------------------------------------------------------------
     def _detect_sparse_device(self, x, top_k: int, detection_threshold: float, div255: bool = False):
-        """Whole sparse extraction on the device, fixed-capacity outputs, no host sync.
+        """Whole sparse extraction on the device, fixed-capacity outputs, no host sync.  `x` is one image batch or a list
+        of batches of identical shape (they are normalised into one activation batch without concatenating the inputs).
         Returns dict of device tensors: keypoints (B,k,2), scores (B,k), descriptors (B,k,64), n_valid (B) int32."""
-        x = self._to_bchw(x)
-        B, _, Hi, Wi = x.shape
+        xs = [self._to_bchw(t) for t in (x if isinstance(x, (list, tuple)) else [x])]
+        _, _, Hi, Wi = xs[0].shape
+        if any(t.shape[1:] != xs[0].shape[1:] for t in xs):
+            raise RuntimeError("image batches must share (C,H,W)")
+        B = sum(t.shape[0] for t in xs)
         H, W = (Hi // 32) * 32, (Wi // 32) * 32
         if H == 0 or W == 0:
             raise RuntimeError("image smaller than 32 pixels")
         rh, rw = Hi / H, Wi / W                                     # python floats, as xfeat.py:237
-        xn = self._preprocess(x, H, W, div255)
+        xn = self._empty((B, H, W))
+        o = 0
+        for t in xs:
+            self._preprocess(t, H, W, div255, out=xn[o:o + t.shape[0]])
+            o += t.shape[0]
         feats, heat, rel, _ = self._run_net(xn, B, H, W)
         kpts = self._empty((B, top_k, 2))
         scores = self._empty((B, top_k))
@@ -244,7 +252,7 @@ class XFeat:
         x1, x2 = self._to_bchw(imgs1), self._to_bchw(imgs2)
         B = x1.shape[0]
         if x1.shape == x2.shape and x1.dtype == x2.dtype:
-            o = self._detect_sparse_device(torch.cat([x1, x2], 0), top_k, self.detection_threshold, div255)
+            o = self._detect_sparse_device([x1, x2], top_k, self.detection_threshold, div255)
             k1, k2 = o["keypoints"][:B], o["keypoints"][B:]
             d1, d2 = o["descriptors"][:B], o["descriptors"][B:]
             n1, n2 = o["n_valid"][:B], o["n_valid"][B:]

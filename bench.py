@@ -168,8 +168,7 @@ def run_gpu(args):
     mnn_events = []
 
     def step_resident(record=False):
-        xcat = torch.cat([d1, d2], 0)
-        o = xf._detect_sparse_device(xcat, TOPK, xf.detection_threshold)
+        o = xf._detect_sparse_device([d1, d2], TOPK, xf.detection_threshold)
         k1, k2 = o["keypoints"][:BATCH], o["keypoints"][BATCH:]
         f1, f2 = o["descriptors"][:BATCH], o["descriptors"][BATCH:]
         n1, n2 = o["n_valid"][:BATCH], o["n_valid"][BATCH:]

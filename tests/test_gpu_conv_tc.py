@@ -32,34 +32,42 @@ def relerr(a, b):
     return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))
 
 
-CASES = [  # (layer id, oracle prefix, basic layer?, H, W, pad)
-    (8, "block3.1", True, 60, 80, 1), (8, "block3.1", True, 13, 21, 1), (8, "block3.1", True, 8, 16, 1),
-    (9, "block3.2", True, 60, 80, 0), (11, "block4.1", True, 30, 40, 1), (12, "block4.2", True, 15, 20, 1),
-    (17, "block_fusion.0", True, 36, 48, 1), (19, "block_fusion.2", False, 12, 16, 0), (20, "heatmap_head.0", True, 7, 130, 0),
-    (25, "keypoint_head.2", True, 60, 80, 0),
+CASES = [  # (layer id, oracle prefix, basic layer?, H_in, W_in, pad, stride)
+    (8, "block3.1", True, 60, 80, 1, 1), (8, "block3.1", True, 13, 21, 1, 1), (8, "block3.1", True, 8, 16, 1, 1),
+    (9, "block3.2", True, 60, 80, 0, 1), (11, "block4.1", True, 30, 40, 1, 1), (12, "block4.2", True, 15, 20, 1, 1),
+    (17, "block_fusion.0", True, 36, 48, 1, 1), (19, "block_fusion.2", False, 12, 16, 0, 1),
+    (20, "heatmap_head.0", True, 7, 130, 0, 1), (25, "keypoint_head.2", True, 60, 80, 0, 1),
+    # channel-padded (24 -> 32) and strided (TMA element strides) variants
+    (5, "block2.0", True, 120, 160, 1, 1), (6, "block2.1", True, 24, 40, 1, 1), (5, "block2.0", True, 9, 13, 1, 1),
+    (7, "block3.0", True, 120, 160, 1, 2), (7, "block3.0", True, 24, 40, 1, 2),
+    (10, "block4.0", True, 60, 80, 1, 2), (10, "block4.0", True, 20, 80, 1, 2),
+    (13, "block5.0", True, 30, 40, 1, 2), (13, "block5.0", True, 10, 40, 1, 2),
 ]
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: f"L{c[0]}_{c[1]}_{c[3]}x{c[4]}")
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"L{c[0]}_{c[1]}_{c[3]}x{c[4]}s{c[6]}")
 def test_conv_tc_layer_vs_oracle(xf, oracle_state, case):
     from accelerated_features_b200 import _lib
-    layer, prefix, basic, H, W, pad = case
+    layer, prefix, basic, H, W, pad, stride = case
     sd = oracle_state
+    wkey = prefix + (".layer.0.weight" if basic else ".weight")
+    cout, cin = sd[wkey].shape[0], sd[wkey].shape[1]
     g = torch.Generator().manual_seed(layer * 1000 + H)
     B = 3
-    x = torch.randn(B, 64, H, W, generator=g) * 2.0
+    x = torch.randn(B, cin, H, W, generator=g) * 2.0
     x[0, :, 0, 0] = 0.0                      # exact zeros and tiny values exercise the lo-term range
     x[1, :, -1, -1] *= 1e-3
-    want = orc._basic_layer(sd, prefix, x, 1, pad) if basic else F.conv2d(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
+    want = orc._basic_layer(sd, prefix, x, stride, pad) if basic else F.conv2d(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
+    Ho, Wo = want.shape[2], want.shape[3]
     xin = x.permute(0, 2, 3, 1).contiguous().cuda()
-    out = torch.empty((B, H, W, 64), device="cuda")
+    out = torch.empty((B, Ho, Wo, cout), device="cuda")
     scratch = torch.empty(B * H * W * 256, dtype=torch.uint8, device="cuda")
     _lib.check(xf._lib.xfeat_debug_conv_layer_tc(xf._ctx, layer, xin.data_ptr(), B, H, W, out.data_ptr(), scratch.data_ptr(),
                                                  scratch.numel(), torch.cuda.current_stream().cuda_stream), "conv_tc")
     torch.cuda.synchronize()
     got = out.permute(0, 3, 1, 2).cpu()
     err = relerr(got, want)
-    print(f"{prefix} {H}x{W}: rel err {err:.2e}")
+    print(f"{prefix} {H}x{W} s{stride}: rel err {err:.2e}")
     assert err < 1e-5, (prefix, err)         # 3-term fp16 split: ~2^-21 operand error + fp32 accumulation
 
 
