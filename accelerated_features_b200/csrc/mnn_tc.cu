@@ -33,8 +33,8 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 constexpr int TC_ROWS = 256, TC_BN = 128, TC_KP = 192, TC_BOX_BYTES = 128 * 128;  // 128 rows x 128 B
-constexpr int TC_THREADS = 192;
-constexpr size_t TC_SMEM = 1024 + 12 * (size_t)TC_BOX_BYTES + 256;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr size_t TC_SMEM = 1024 + 12 * (size_t)TC_BOX_BYTES + 256 + 2 * 128 * 8;
 
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ f, const int* __restrict__ np, int n_max,
                                                      int64_t stride, unsigned* __restrict__ out) {
@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
   uint64_t* acc_full = bars + 5;   // [2]
   uint64_t* acc_empty = bars + 7;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  unsigned long long* sMerge = reinterpret_cast<unsigned long long*>(bars + 12);   // [2 slabs][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = (n_cols + TC_BN - 1) / TC_BN;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
       tc::mbar_init(&b_full[i], 1);
       tc::mbar_init(&b_empty[i], 1);
       tc::mbar_init(&acc_full[i], 1);
-      tc::mbar_init(&acc_empty[i], 4);
+      tc::mbar_init(&acc_empty[i], 8);
     }
     tc::fence_barrier_init();
   }
@@ -182,51 +183,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
     __syncwarp();
   } else {
     // ---------------- epilogue: running row arg-max ----------------
-    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    // warps 2-9: TMEM lane quarter q = warp & 3 (hardware rule: a warp reaches lanes 32*(warp%4)..+31), column half
+    // hc = (warp - 2) >> 2 of each 128-column slab.  tcgen05.ld of chunk c+1 is in flight while chunk c is reduced.
+    const int q = warp & 3, hc = (warp - 2) >> 2;
     float best[2] = {-INFINITY, -INFINITY};
     uint32_t bidx[2] = {0xffffffffu, 0xffffffffu};
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    auto reduce_chunk = [&](const uint32_t (&r)[32], int col0, int slab) {
+      if (col0 + 32 <= n_cols) {
+        float m = __uint_as_float(r[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+        if (m > best[slab]) {            // strict: earlier columns win ties (torch.max / argmax rule)
+          int j0 = 31;
+#pragma unroll
+          for (int j = 30; j >= 0; --j)
+            if (__uint_as_float(r[j]) == m) j0 = j;
+          best[slab] = m;
+          bidx[slab] = (uint32_t)(col0 + j0);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]);
+          if (col0 + j < n_cols && v > best[slab]) { best[slab] = v; bidx[slab] = (uint32_t)(col0 + j); }
+        }
+      }
+    };
     for (int t = 0; t < T; ++t) {
       const int s = t & 1, ph = (t >> 1) & 1;
       tc::mbar_wait(&acc_full[s], ph);
       tc::tc_fence_after();
-#pragma unroll
-      for (int slab = 0; slab < 2; ++slab) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          __syncwarp();                  // tcgen05.ld is .sync.aligned: reconverge after the data-dependent branch below
-          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + s * 256 + slab * 128 + c * 32, r);
-          tc::tmem_ld_wait();
-          const int col0 = t * TC_BN + c * 32;
-          if (col0 + 32 <= n_cols) {
-            float m = __uint_as_float(r[0]);
-#pragma unroll
-            for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-            if (m > best[slab]) {        // strict: earlier columns win ties (torch.max / argmax rule)
-              int j0 = 31;
-#pragma unroll
-              for (int j = 30; j >= 0; --j)
-                if (__uint_as_float(r[j]) == m) j0 = j;
-              best[slab] = m;
-              bidx[slab] = (uint32_t)(col0 + j0);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(r[j]);
-              if (col0 + j < n_cols && v > best[slab]) { best[slab] = v; bidx[slab] = (uint32_t)(col0 + j); }
-            }
-          }
-        }
-      }
+      // this warp's 4 chunks of the tile: (slab 0, cols hc*64 + {0,32}), (slab 1, cols hc*64 + {0,32})
+      uint32_t ra[32], rb[32];
+      const uint32_t tb = lane_addr + s * 256 + hc * 64;
+      const int cb = t * TC_BN + hc * 64;
+      __syncwarp();
+      tc::tmem_ld_32x32(tb, ra);
+      tc::tmem_ld_wait();
+      __syncwarp();
+      tc::tmem_ld_32x32(tb + 32, rb);
+      reduce_chunk(ra, cb, 0);
+      tc::tmem_ld_wait();
+      __syncwarp();
+      tc::tmem_ld_32x32(tb + 128, ra);
+      reduce_chunk(rb, cb + 32, 0);
+      tc::tmem_ld_wait();
+      __syncwarp();
+      tc::tmem_ld_32x32(tb + 128 + 32, rb);
+      reduce_chunk(ra, cb, 1);
+      tc::tmem_ld_wait();
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&acc_empty[s]);
+      if (lane == 0) tc::mbar_arrive(&acc_empty[s]);   // all TMEM reads of this buffer are done
+      reduce_chunk(rb, cb + 32, 1);
     }
+    // merge the two column halves of every row (lower column index wins ties through the packed compare)
+    unsigned long long pk[2];
 #pragma unroll
-    for (int slab = 0; slab < 2; ++slab) {
-      const int row = row0 + slab * 128 + q * 32 + lane;
-      if (row < n_rows) out[(int64_t)pair * out_stride + row] = (bidx[slab] == 0xffffffffu) ? 0ull : pack_vi(best[slab], bidx[slab]);
+    for (int slab = 0; slab < 2; ++slab) pk[slab] = (bidx[slab] == 0xffffffffu) ? 0ull : pack_vi(best[slab], bidx[slab]);
+    if (hc == 1) {
+      sMerge[0 * 128 + q * 32 + lane] = pk[0];
+      sMerge[1 * 128 + q * 32 + lane] = pk[1];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
+    if (hc == 0) {
+#pragma unroll
+      for (int slab = 0; slab < 2; ++slab) {
+        const unsigned long long o = sMerge[slab * 128 + q * 32 + lane];
+        const unsigned long long m = o > pk[slab] ? o : pk[slab];
+        const int row = row0 + slab * 128 + q * 32 + lane;
+        if (row < n_rows) out[(int64_t)pair * out_stride + row] = m;
+      }
     }
   }
   tc::tc_fence_before();

@@ -23,10 +23,15 @@ xf = XFeat(top_k=4096)
 g = torch.Generator().manual_seed(0)
 x1 = torch.randn(a.batch, 3, a.height, a.width, generator=g).cuda()
 x2 = torch.randn(a.batch, 3, a.height, a.width, generator=g).cuda()
+import time
 for i in range(a.steps):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
     if a.workload == "sparse":
         mk0, mk1, cnt = xf._match_sparse_batch_device(x1, x2, 4096, -1)
     else:
         m, n = xf._match_star_device(x1, x2, 4096)
     torch.cuda.synchronize()
+    print(f"step {i}: {1e3 * (time.perf_counter() - t0):.2f} ms, peak mem {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB", flush=True)
+if a.workload == "star":
+    print("refined matches per pair (first 8):", n[:8].tolist())
 print("done", a.workload, a.steps)
