@@ -9,7 +9,7 @@ namespace xf {
 
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
-static int g_conv_impl = 1;  // 0 = fp32 CUDA-core convs everywhere, 1 = tcgen05 for the 64->64 stride-1 layers (default)
+int g_conv_impl = 2;  // 0 = fp32 CUDA-core convs everywhere, 1 = tcgen05 for the 64->64 stride-1 layers (default)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -95,7 +95,7 @@ extern "C" int xfeat_create(xfeat_ctx** out, int device, const float* packed_hos
   return XF_OK;
 }
 
-extern "C" void xfeat_set_conv_impl(int impl) { xf::g_conv_impl = impl ? 1 : 0; }
+extern "C" void xfeat_set_conv_impl(int impl) { xf::g_conv_impl = (impl < 0 || impl > 2) ? 1 : impl; }
 extern "C" int xfeat_get_conv_impl(void) { return xf::g_conv_impl; }
 
 extern "C" void xfeat_destroy(xfeat_ctx* ctx) {

@@ -131,7 +131,10 @@ namespace xf {
 enum { IN_NHWC = 0, IN_UNFOLD8 = 1 };
 int launch_conv_layer(const xfeat_ctx* ctx, int layer, const float* in, int in_mode, int B, int Hi, int Wi,
                       float* out, cudaStream_t st, const int* n_live = nullptr, __half* out_split = nullptr);
+extern int g_conv_impl;  // 0 = fp32 CUDA cores, 1 = tcgen05 (per-tap operand loads), 2 = tcgen05 + halo-patch reuse for 3x3/s1
 bool conv_tc_eligible(int layer);
+int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int H, int W, __half* out_split,
+                        float* out_f32, cudaStream_t st);
 int conv_tc_prepare(xfeat_ctx* ctx);
 int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int H, int W, __half* out_split,
                    float* out_f32, cudaStream_t st);

@@ -407,6 +407,8 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
   XF_REQUIRE(tc_layer_cfg(layer, c) && ctx->d_tcw, "conv_tc: layer %d not prepared for the tensor-core path", layer);
   XF_REQUIRE(out_split || out_f32, "conv_tc: no output");
   XF_REQUIRE(!(out_split && c.ntiles > 1), "conv_tc: split output needs a single N tile");
+  if (g_conv_impl == 2 && kLayers[layer].ks == 3 && kLayers[layer].stride == 1 && c.ntiles == 1 && c.cinp == c.nout)
+    return launch_conv_tc_halo(ctx, layer, in_split, B, Hin, Win, out_split, out_f32, st);
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");

@@ -1,0 +1,338 @@
+// 3x3 / stride-1 convolution on tcgen05 with HALO-PATCH operand reuse.
+//
+// conv_tc_kernel re-reads the input patch once per tap (9x the activation bytes through L2).  Here the haloed patch
+// (TH+2) x (TW+2) pixels is loaded ONCE per tile by a single 4-D TMA box into a 128B-swizzled K-major array whose rows
+// are the patch pixels in raster order (pitch PW = TW + 2).  If the GEMM rows are enumerated with the same pitch,
+//      m = h * PW + w      (h < TH, w < PW; columns w >= TW are junk lanes that are never stored)
+// then the A operand of tap (dy,dx) is the SAME array shifted by a constant number of rows:
+//      row(m, tap) = m + dy * PW + dx
+// i.e. the tap is selected by advancing the shared-memory matrix descriptor's start address by (dy*PW+dx)*128 bytes
+// (not 1024-aligned in general; measured on B200: the 128B swizzle is applied on physical address bits, so the shifted
+// descriptor keeps base_offset = 0 -- see tests/test_gpu_conv_halo.py, which checks both settings).
+// TH * PW <= 128, so a tile yields TH*TW valid pixels out of 128 MMA rows (TW = 40: 120/128).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace xf {
+
+constexpr int CH_THREADS = 192;
+constexpr int CH_PATCH_BYTES = 34816;   // >= (2*PW + 2 + 128) * 128 for PW <= 66, multiple of 1024
+
+template <int CINP, int NOUT>
+struct HaloCfg {
+  static constexpr int W_GROUP = NOUT * 128;
+  static constexpr size_t W_BYTES = (size_t)9 * 2 * W_GROUP;
+  static constexpr size_t SMEM = 1024 + W_BYTES + 2 * (size_t)CH_PATCH_BYTES + 768;
+  static constexpr int TMEM_COLS = 2 * NOUT;
+};
+
+struct HaloParams {
+  CUtensorMap amap;   // (B,H,W,2*CINP) halves; box {64, PW, TH+2, 1}
+  CUtensorMap wmap;
+  const float* bias;
+  float inv_wscale;
+  int B, H, W;
+  int TW, TH, PW;
+  __half* out_split;
+  float* out_f32;
+  int f32_c, n_real;
+  int relu;
+  int desc_mode;      // 0 (default, correct on B200): base_offset = 0; 1: base_offset = (addr >> 7) & 7 (bring-up experiment)
+};
+
+__device__ __forceinline__ uint64_t make_desc_sw128_at(uint32_t smem_addr, uint32_t sbo_bytes, int mode) {
+  uint64_t d = tc::make_desc_sw128(smem_addr, sbo_bytes);
+  if (mode) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
+  return d;
+}
+
+template <int CINP, int NOUT>
+__global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ HaloParams P) {
+  using C = HaloCfg<CINP, NOUT>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sW = base;
+  unsigned char* sP = base + C::W_BYTES;                     // two patch buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + C::W_BYTES + 2 * CH_PATCH_BYTES);
+  uint64_t* w_full = bars;
+  uint64_t* p_full = bars + 1;     // [2]
+  uint64_t* p_empty = bars + 3;    // [2]
+  uint64_t* acc_full = bars + 5;   // [2]
+  uint64_t* acc_empty = bars + 7;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* sBias = reinterpret_cast<float*>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_x = (P.W + P.TW - 1) / P.TW, tiles_y = (P.H + P.TH - 1) / P.TH;
+  const int tiles_img = tiles_x * tiles_y;
+  const int n_tiles = tiles_img * P.B;
+  const uint32_t patch_tx = (uint32_t)(P.TH + 2) * P.PW * 128;
+
+  if (threadIdx.x < NOUT) sBias[threadIdx.x] = (threadIdx.x < P.n_real) ? __ldg(P.bias + threadIdx.x) : 0.f;
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&P.amap);
+    tc::tma_prefetch_desc(&P.wmap);
+    tc::mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&p_full[i], 1);
+      tc::mbar_init(&p_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // CINP = 64: buffer 0 = hi patch, buffer 1 = lo patch of the SAME tile (each single-buffered; the hi-only MMAs of a
+  //            tile run first so the next tile's hi patch can stream in while the lo MMAs run, and vice versa).
+  // CINP = 32: buffers 0/1 alternate between tiles (rows are [hi(32)|lo(32)]).
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_expect_tx(w_full, (uint32_t)C::W_BYTES);
+      for (int i = 0; i < 18; ++i) tc::tma_load_2d(sW + (size_t)i * C::W_GROUP, &P.wmap, w_full, 0, i * NOUT);
+      uint32_t tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const int b = tile / tiles_img, rem = tile - b * tiles_img;
+        const int y0 = (rem / tiles_x) * P.TH - 1, x0 = (rem % tiles_x) * P.TW - 1;
+        if (CINP == 64) {
+          const uint32_t ph = tcount & 1;
+          tc::mbar_wait(&p_empty[0], ph ^ 1);
+          tc::mbar_expect_tx(&p_full[0], patch_tx);
+          tc::tma_load_4d(sP, &P.amap, &p_full[0], 0, x0, y0, b);
+          tc::mbar_wait(&p_empty[1], ph ^ 1);
+          tc::mbar_expect_tx(&p_full[1], patch_tx);
+          tc::tma_load_4d(sP + CH_PATCH_BYTES, &P.amap, &p_full[1], 64, x0, y0, b);
+        } else {
+          const int s = tcount & 1;
+          tc::mbar_wait(&p_empty[s], ((tcount >> 1) & 1) ^ 1);
+          tc::mbar_expect_tx(&p_full[s], patch_tx);
+          tc::tma_load_4d(sP + (size_t)s * CH_PATCH_BYTES, &P.amap, &p_full[s], 0, x0, y0, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);
+      tc::mbar_wait(w_full, 0);
+      const uint32_t w_base = tc::smem_u32(sW);
+      uint32_t tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const int a = tcount & 1;
+        tc::mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d = tmem + a * NOUT;
+        if (CINP == 64) {
+          const uint32_t ph = tcount & 1;
+          const uint32_t hi_base = tc::smem_u32(sP), lo_base = hi_base + CH_PATCH_BYTES;
+          tc::mbar_wait(&p_full[0], ph);
+          tc::tc_fence_after();
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * 128u;
+            const uint64_t ahi = make_desc_sw128_at(hi_base + shift, 1024, P.desc_mode);
+            const uint64_t whi = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2) * C::W_GROUP, 1024);
+            const uint64_t wlo = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2 + 1) * C::W_GROUP, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, whi + 2 * k, idesc, (tap | k) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
+          }
+          tc::umma_commit(&p_empty[0]);            // hi patch may be overwritten once these MMAs retire
+          tc::mbar_wait(&p_full[1], ph);
+          tc::tc_fence_after();
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * 128u;
+            const uint64_t alo = make_desc_sw128_at(lo_base + shift, 1024, P.desc_mode);
+            const uint64_t whi = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2) * C::W_GROUP, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, alo + 2 * k, whi + 2 * k, idesc, 1u);
+          }
+          tc::umma_commit(&p_empty[1]);
+        } else {
+          const int s = tcount & 1;
+          const uint32_t p_base = tc::smem_u32(sP) + (uint32_t)s * CH_PATCH_BYTES;
+          tc::mbar_wait(&p_full[s], (tcount >> 1) & 1);
+          tc::tc_fence_after();
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * 128u;
+            const uint64_t a0 = make_desc_sw128_at(p_base + shift, 1024, P.desc_mode);
+            const uint64_t w0 = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2) * C::W_GROUP, 1024);
+            const uint64_t w1 = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2 + 1) * C::W_GROUP, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc, (tap | k) ? 1u : 0u);   // [hi|lo].[whi|whi]
+#pragma unroll
+            for (int k = 0; k < 2; ++k) tc::umma_f16(d, a0 + 2 * k, w1 + 2 * k, idesc, 1u);                    // hi . wlo
+          }
+          tc::umma_commit(&p_empty[s]);
+        }
+        tc::umma_commit(&acc_full[a]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int mh = m / P.PW, mw = m - mh * P.PW;
+    const bool lane_ok = (mh < P.TH) && (mw < P.TW);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int a = tcount & 1;
+      const int b = tile / tiles_img, rem = tile - b * tiles_img;
+      const int y = (rem / tiles_x) * P.TH + mh, x = (rem % tiles_x) * P.TW + mw;
+      tc::mbar_wait(&acc_full[a], (tcount >> 1) & 1);
+      tc::tc_fence_after();
+      uint32_t v[NOUT];
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < NOUT / 32; ++c) {
+        uint32_t t[32];
+        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * NOUT + c * 32, t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[c * 32 + j] = t[j];
+      }
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
+      if (lane_ok && y < P.H && x < P.W) {
+        const int64_t pix = ((int64_t)b * P.H + y) * P.W + x;
+        float o[NOUT];
+#pragma unroll
+        for (int c = 0; c < NOUT; ++c) {
+          float t0 = fmaf(__uint_as_float(v[c]), P.inv_wscale, sBias[c]);
+          if (P.relu) t0 = fmaxf(t0, 0.f);
+          o[c] = t0;
+        }
+        if (P.out_f32) {
+          float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * P.f32_c);
+#pragma unroll
+          for (int c = 0; c < NOUT / 4; ++c)
+            if (4 * c < P.n_real) op[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        }
+        if (P.out_split) {
+          uint4* hp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * NOUT));
+#pragma unroll
+          for (int c = 0; c < NOUT / 8; ++c) {
+            __half2 h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x0 = o[8 * c + 2 * j], x1 = o[8 * c + 2 * j + 1];
+              h[j] = __floats2half2_rn(x0, x1);
+              const float2 hf = __half22float2(h[j]);
+              l[j] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            }
+            hp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                               *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+            hp[NOUT / 8 + c] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                                          *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, C::TMEM_COLS);
+  }
+}
+
+// tile geometry: TW <= 64 (PW <= 66), TH = 128 / PW; minimise MMA rows spent per valid output pixel
+static void pick_halo_tile(int H, int W, int& TW, int& TH) {
+  double best = 1e30;
+  TW = 16; TH = 7;
+  for (int tw = 8; tw <= 64; ++tw) {
+    const int pw = tw + 2, th = 128 / pw;
+    if (th < 1) continue;
+    const double tiles = (double)cdiv(W, tw) * cdiv(H, th);
+    const double cost = tiles * (128.0 + 0.15 * (th + 2) * pw);   // MMA rows + a term for the patch bytes
+    if (cost < best) { best = cost; TW = tw; TH = th; }
+  }
+}
+
+int g_halo_desc_mode = 0;   // measured on B200: the UMMA swizzle is a function of the physical shared-memory address, so a
+                            // start address shifted by whole 128-byte rows needs base_offset = 0 (mode 1 gives wrong results)
+
+// same contract as launch_conv_tc, for 3x3 stride-1 layers with (CINP,NOUT) in {(64,64), (32,32)}
+int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int H, int W, __half* out_split,
+                        float* out_f32, cudaStream_t st) {
+  const LayerSpec& sp = kLayers[layer];
+  XF_REQUIRE(sp.ks == 3 && sp.stride == 1 && ctx->d_tcw && ctx->tc_off[layer] != (size_t)-1,
+             "conv_tc_halo: layer %d is not a prepared 3x3 stride-1 layer", layer);
+  const bool c64 = (sp.cin == 64 && sp.cout == 64), c32 = (sp.cin == 24 && sp.cout == 24);
+  XF_REQUIRE(c64 || c32, "conv_tc_halo: unsupported channel configuration");
+  const int cinp = c64 ? 64 : 32, nout = cinp;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return XF_E_CUDA;
+  }
+  HaloParams P;
+  pick_halo_tile(H, W, P.TW, P.TH);
+  P.PW = P.TW + 2;
+  const cuuint64_t row_bytes = (cuuint64_t)2 * cinp * sizeof(__half);
+  const cuuint64_t dims[4] = {(cuuint64_t)2 * cinp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {row_bytes, (cuuint64_t)W * row_bytes, (cuuint64_t)H * W * row_bytes};
+  const cuuint32_t box[4] = {64, (cuuint32_t)P.PW, (cuuint32_t)(P.TH + 2), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&P.amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)in_split, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(halo activations) failed: %d", (int)r);
+    return XF_E_CUDA;
+  }
+  const cuuint64_t wdims[2] = {64, (cuuint64_t)18 * nout};
+  const cuuint64_t wstrides[1] = {128};
+  const cuuint32_t wbox[2] = {64, (cuuint32_t)nout};
+  const cuuint32_t westr[2] = {1, 1};
+  r = enc(&P.wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)((__half*)ctx->d_tcw + ctx->tc_off[layer]), wdims, wstrides, wbox,
+          westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(halo weights) failed: %d", (int)r);
+    return XF_E_CUDA;
+  }
+  P.bias = ctx->d_weights + ctx->table.b_off[layer];
+  P.inv_wscale = ctx->tc_inv_wscale[layer];
+  P.B = B; P.H = H; P.W = W;
+  P.out_split = out_split;
+  P.out_f32 = out_f32;
+  P.f32_c = sp.cout;
+  P.n_real = sp.cout;
+  P.relu = sp.relu;
+  P.desc_mode = g_halo_desc_mode;
+  const int n_tiles = cdiv(H, P.TH) * cdiv(W, P.TW) * B;
+  const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
+  if (c64) {
+    static bool attr = false;
+    if (!attr) {
+      XF_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HaloCfg<64, 64>::SMEM));
+      attr = true;
+    }
+    conv_tc_halo_kernel<64, 64><<<grid, CH_THREADS, HaloCfg<64, 64>::SMEM, st>>>(P);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      XF_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HaloCfg<32, 32>::SMEM));
+      attr = true;
+    }
+    conv_tc_halo_kernel<32, 32><<<grid, CH_THREADS, HaloCfg<32, 32>::SMEM, st>>>(P);
+  }
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+}  // namespace xf
+
+extern "C" void xfeat_set_halo_desc_mode(int mode) { xf::g_halo_desc_mode = mode; }

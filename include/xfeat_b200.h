@@ -79,8 +79,10 @@ XF_API int xfeat_preprocess(const void* d_img, int dtype, int B, int C, int Hi, 
                      int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255,
                      int H, int W, float* d_xn, double* d_stats, void* stream);
 
-/* Implementation switch of the 64->64 stride-1 conv layers inside xfeat_net (process-wide): 0 = fp32 CUDA-core kernels,
- * 1 = tcgen05 tensor-core kernel (split-fp16 operands, fp32 accumulation in TMEM). */
+/* Implementation switch of the conv layers inside xfeat_net (process-wide): 0 = fp32 CUDA-core kernels everywhere,
+ * 1 = tcgen05 tensor-core kernels (split-fp16 operands, fp32 accumulation in TMEM), 2 = as 1 plus halo-patch operand
+ * reuse for the 3x3 stride-1 layers.  xfeat_set_halo_desc_mode is a bring-up knob of mode 2 (1 = PTX base_offset rule). */
+XF_API void xfeat_set_halo_desc_mode(int mode);
 XF_API void xfeat_set_conv_impl(int impl);
 XF_API int xfeat_get_conv_impl(void);
 XF_API size_t xfeat_net_workspace_bytes(int B, int H, int W);

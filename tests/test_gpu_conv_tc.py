@@ -71,8 +71,9 @@ def test_conv_tc_layer_vs_oracle(xf, oracle_state, case):
     assert err < 1e-5, (prefix, err)         # 3-term fp16 split: ~2^-21 operand error + fp32 accumulation
 
 
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("which", ["g3_small", "vga"])
-def test_net_tc_vs_oracle(xf, oracle_state, golden, assets_vga, which):
+def test_net_tc_vs_oracle(xf, oracle_state, golden, assets_vga, which, impl):
     if which == "g3_small":
         x = torch.from_numpy(golden("g3_randn_small.npz")["x"])
     else:
@@ -81,7 +82,7 @@ def test_net_tc_vs_oracle(xf, oracle_state, golden, assets_vga, which):
     st = orc.backbone(oracle_state, x)
     B, _, H, W = x.shape
     xn = st["xn"][:, 0].contiguous().cuda()
-    with conv_impl(xf, 1):
+    with conv_impl(xf, impl):
         feats, heat, rel, logits = xf._run_net(xn, B, H, W, want_logits=True)
         torch.cuda.synchronize()
     with conv_impl(xf, 0):
@@ -91,7 +92,7 @@ def test_net_tc_vs_oracle(xf, oracle_state, golden, assets_vga, which):
     e_log = (logits.permute(0, 3, 1, 2).cpu() - st["kpt_logits"]).abs().max().item()
     e_rel = (rel.cpu() - st["reliability"][:, 0]).abs().max().item()
     e_heat = (heat.cpu() - orc.kpts_heatmap(st["kpt_logits"])[:, 0]).abs().max().item()
-    print(f"[{which}] tcgen05: feats rel {e_feats:.2e} logits abs {e_log:.2e} reliability abs {e_rel:.2e} heat abs {e_heat:.2e}; "
+    print(f"[{which}] tcgen05 impl {impl}: feats rel {e_feats:.2e} logits abs {e_log:.2e} reliability abs {e_rel:.2e} heat abs {e_heat:.2e}; "
           f"vs simt feats rel {relerr(feats, feats0):.2e}")
     # 3-term fp16 split carries 22 mantissa bits per operand (fp32: 24): a few 1e-5 after ~20 layers, 1e-3 is the budget
     assert e_feats < 1e-4 and e_log < 5e-4 and e_rel < 5e-5 and e_heat < 5e-5
