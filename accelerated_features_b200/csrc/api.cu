@@ -158,12 +158,18 @@ extern "C" int xfeat_net(xfeat_ctx* ctx, const float* d_xn, int B, int H, int W,
     XF_RUN(launch_conv_tc(ctx, L_B4_0, s8a, B, H8, W8, s16a, nullptr, st));                          // block4 (stride 2), model.py:142
     XF_RUN(launch_conv_tc(ctx, L_B4_1, s16a, B, H16, W16, s16b, nullptr, st));
     XF_RUN(launch_conv_tc(ctx, L_B4_2, s16b, B, H16, W16, s16a, ws.x4, st));   // x4: fp32 for the fusion, split for block5.0
-    XF_RUN(launch_conv_tc(ctx, L_B5_0, s16a, B, H16, W16, nullptr, ws.t32a, st));                    // block5 (stride 2), model.py:143
+    // block5: 128 channels, split tensors are [hi(128) | lo(128)] = 512 B per pixel            model.py:143
+    __half *s32a = (__half*)ws.t32a, *s32b = (__half*)ws.t32b;
+    XF_RUN(launch_conv_tc(ctx, L_B5_0, s16a, B, H16, W16, s32a, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_B5_1, s32a, B, H32, W32, s32b, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_B5_2, s32b, B, H32, W32, s32a, nullptr, st));
+    XF_RUN(launch_conv_tc(ctx, L_B5_3, s32a, B, H32, W32, nullptr, ws.x5, st));
   }
-  // rest of block5 (128 channels: fp32 CUDA-core kernel)                         model.py:143
-  XF_RUN(launch_conv_layer(ctx, L_B5_1, ws.t32a, IN_NHWC, B, H32, W32, ws.t32b, st));
-  XF_RUN(launch_conv_layer(ctx, L_B5_2, ws.t32b, IN_NHWC, B, H32, W32, ws.t32a, st));
-  XF_RUN(launch_conv_layer(ctx, L_B5_3, ws.t32a, IN_NHWC, B, H32, W32, ws.x5, st));
+  if (g_conv_impl == 0) {   // rest of block5 on the fp32 CUDA-core kernel                  model.py:143
+    XF_RUN(launch_conv_layer(ctx, L_B5_1, ws.t32a, IN_NHWC, B, H32, W32, ws.t32b, st));
+    XF_RUN(launch_conv_layer(ctx, L_B5_2, ws.t32b, IN_NHWC, B, H32, W32, ws.t32a, st));
+    XF_RUN(launch_conv_layer(ctx, L_B5_3, ws.t32a, IN_NHWC, B, H32, W32, ws.x5, st));
+  }
   if (g_conv_impl == 0) {
     // pyramid fusion                                                             model.py:146-148
     XF_RUN(launch_fuse_pyramid(ws.x3, ws.x4, ws.x5, ws.fin, nullptr, B, H8, W8, st));

@@ -212,8 +212,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             if (4 * c < P.n_real) op[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
         }
         if (P.out_split) {
-          // [hi(split_c) | lo(split_c)]; this kernel only produces split_c == NOUT (padded channels are exact zeros)
-          uint4* hp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * NOUT));
+          // [hi(split_c) | lo(split_c)]; this N tile owns channels f32_co0 .. f32_co0+NOUT-1 (padded channels: exact zeros)
+          uint4* hp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * P.split_c) + P.f32_co0);
+          uint4* lp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * P.split_c) + P.split_c + P.f32_co0);
 #pragma unroll
           for (int c = 0; c < NOUT / 8; ++c) {
             __half2 h[4], l[4];
@@ -226,8 +227,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             }
             hp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
                                *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
-            hp[NOUT / 8 + c] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
-                                          *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
+            lp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                               *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
           }
         }
       }
@@ -238,6 +239,176 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == 1) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 128-input-channel layers (block5.1, block5.2 3x3; block5.3 1x1): the weights of all taps no longer fit in shared memory,
+// so each pipeline stage carries one tap of BOTH operands: A = {hi0, hi1, lo0, lo1} boxes (128 px x 64 halves each) and
+// W = {whi0, wlo0, whi1, wlo1} (64 cout x 64 halves each) of this CTA's 64-channel N tile (blockIdx.y).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int C128_WBOX = 64 * 128;
+constexpr int C128_STAGE = 4 * CT_ABOX + 4 * C128_WBOX;   // 96 KB
+constexpr size_t C128_SMEM = 1024 + 2 * (size_t)C128_STAGE + 768;
+
+template <int KS>
+__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_constant__ ConvTcParams P) {
+  constexpr int TAPS = KS * KS, NOUT = 64, NS = 2;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sS = base;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + NS * (size_t)C128_STAGE);
+  uint64_t* s_full = bars;           // [NS]
+  uint64_t* s_empty = bars + NS;     // [NS]
+  uint64_t* acc_full = bars + 2 * NS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sBias = reinterpret_cast<float*>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int TW = 1 << P.tw_log2, TH = 128 >> P.tw_log2;
+  const int tiles_x = (P.W + TW - 1) / TW, tiles_y = (P.H + TH - 1) / TH;
+  const int tiles_img = tiles_x * tiles_y;
+  const int n_tiles = tiles_img * P.B;
+  const int nt = blockIdx.y;                     // N tile: output channels nt*64 .. nt*64+63
+  const int co0 = nt * NOUT;
+
+  if (threadIdx.x < NOUT) sBias[threadIdx.x] = __ldg(P.bias + co0 + threadIdx.x);
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&P.amap);
+    tc::tma_prefetch_desc(&P.wmap);
+    for (int i = 0; i < NS; ++i) {
+      tc::mbar_init(&s_full[i], 1);
+      tc::mbar_init(&s_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 128);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_img, rem = tile - b * tiles_img;
+        const int y0 = (rem / tiles_x) * TH - P.pad, x0 = (rem % tiles_x) * TW - P.pad;
+        for (int tap = 0; tap < TAPS; ++tap, ++it) {
+          const int s = it % NS;
+          const int dy = (KS == 3) ? tap / 3 : 0, dx = (KS == 3) ? tap % 3 : 0;
+          tc::mbar_wait(&s_empty[s], ((it / NS) & 1) ^ 1);
+          tc::mbar_expect_tx(&s_full[s], C128_STAGE);
+          unsigned char* dst = sS + (size_t)s * C128_STAGE;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)   // channel blocks hi0, hi1, lo0, lo1 = halves [0,64) [64,128) [128,192) [192,256)
+            tc::tma_load_4d(dst + j * CT_ABOX, &P.amap, &s_full[s], 64 * j, x0 + dx, y0 + dy, b);
+          // weights: rows ((nt * TAPS + tap) * 4 + g) * 64, g = whi0, wlo0, whi1, wlo1 -> one 256-row box
+          tc::tma_load_2d(dst + 4 * CT_ABOX, &P.wmap, &s_full[s], 0, ((nt * TAPS + tap) * 4) * 64);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+        const int a = tcount & 1;
+        tc::mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d = tmem + a * NOUT;
+        for (int tap = 0; tap < TAPS; ++tap, ++it) {
+          const int s = it % NS;
+          tc::mbar_wait(&s_full[s], (it / NS) & 1);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(sS + (size_t)s * C128_STAGE), sw = sa + 4 * CT_ABOX;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t ahi = tc::make_desc_sw128(sa + kb * CT_ABOX, 1024), alo = tc::make_desc_sw128(sa + (2 + kb) * CT_ABOX, 1024);
+            const uint64_t whi = tc::make_desc_sw128(sw + (2 * kb) * C128_WBOX, 1024), wlo = tc::make_desc_sw128(sw + (2 * kb + 1) * C128_WBOX, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, whi + 2 * k, idesc, (tap | kb | k) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, alo + 2 * k, whi + 2 * k, idesc, 1u);
+          }
+          tc::umma_commit(&s_empty[s]);
+        }
+        tc::umma_commit(&acc_full[a]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ph_ = r >> P.tw_log2, pw_ = r & (TW - 1);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      const int a = tcount & 1;
+      const int b = tile / tiles_img, rem = tile - b * tiles_img;
+      const int y = (rem / tiles_x) * TH + ph_, x = (rem % tiles_x) * TW + pw_;
+      tc::mbar_wait(&acc_full[a], (tcount >> 1) & 1);
+      tc::tc_fence_after();
+      uint32_t v0[32], v1[32];
+      __syncwarp();
+      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * NOUT, v0);
+      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * NOUT + 32, v1);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[a]);
+      if (y < P.H && x < P.W) {
+        const int64_t pix = ((int64_t)b * P.H + y) * P.W + x;
+        float o[NOUT];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float t0 = fmaf(__uint_as_float(v0[c]), P.inv_wscale, sBias[c]);
+          float t1 = fmaf(__uint_as_float(v1[c]), P.inv_wscale, sBias[32 + c]);
+          if (P.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
+          o[c] = t0; o[32 + c] = t1;
+        }
+        if (P.out_f32) {
+          float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * P.f32_c + co0);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) op[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        }
+        if (P.out_split) {
+          uint4* hp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * P.split_c) + co0);
+          uint4* lp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * P.split_c) + P.split_c + co0);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            __half2 h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x0 = o[8 * c + 2 * j], x1 = o[8 * c + 2 * j + 1];
+              h[j] = __floats2half2_rn(x0, x1);
+              const float2 hf = __half22float2(h[j]);
+              l[j] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            }
+            hp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                               *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+            lp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                               *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, 128);
   }
 }
 
@@ -321,6 +492,7 @@ static bool tc_layer_cfg(int layer, TcLayer& c) {
   if (s.cin == 24 && s.cout == 24) { c = {32, 32, 1}; return true; }            // block2 (channels padded 24 -> 32)
   if (s.cin == 24 && s.cout == 64) { c = {32, 64, 1}; return true; }            // block3.0 (stride 2)
   if (s.cin == 64 && s.cout == 128) { c = {64, 64, 2}; return true; }           // block5.0 (stride 2), two N tiles
+  if (s.cin == 128 && s.stride == 1) { c = {128, 64, s.cout / 64}; return true; }   // block5.1/5.2 (3x3), block5.3 (1x1): streamed weights
   return false;
 }
 bool conv_tc_eligible(int layer) {
@@ -336,7 +508,7 @@ int conv_tc_prepare(xfeat_ctx* ctx) {
     TcLayer c;
     if (tc_layer_cfg(l, c)) {
       ctx->tc_off[l] = total;
-      total += (size_t)c.ntiles * kLayers[l].ks * kLayers[l].ks * 2 * c.nout * 64;
+      total += (size_t)c.ntiles * kLayers[l].ks * kLayers[l].ks * 2 * c.nout * 64 * (c.cinp == 128 ? 2 : 1);
     }
   }
   std::vector<__half> h(total, __float2half_rn(0.f));
@@ -352,6 +524,23 @@ int conv_tc_prepare(xfeat_ctx* ctx) {
     if (mx > 0.f) frexpf(mx, &e);
     const float s = (mx > 0.f) ? ldexpf(1.f, 13 - e) : 1.f;          // max|w| * s in [2^12, 2^13)
     ctx->tc_inv_wscale[l] = (mx > 0.f) ? ldexpf(1.f, e - 13) : 1.f;
+    if (c.cinp == 128) {
+      for (int nt = 0; nt < c.ntiles; ++nt)
+        for (int t = 0; t < taps; ++t)
+          for (int n = 0; n < 64; ++n) {
+            const int co = nt * 64 + n;
+            for (int ci = 0; ci < 128; ++ci) {
+              const float v = w[((size_t)t * sp.cin + ci) * sp.cout + co] * s;
+              const __half hi = __float2half_rn(v);
+              const __half lo = __float2half_rn(v - __half2float(hi));
+              const int kb = ci >> 6, cc = ci & 63;
+              __half* grp = h.data() + ctx->tc_off[l] + ((((size_t)nt * taps + t) * 4 + 2 * kb) * 64 + n) * 64;
+              grp[cc] = hi;                 // group 2*kb   : whi of K block kb
+              grp[64 * 64 + cc] = lo;       // group 2*kb+1 : wlo of K block kb
+            }
+          }
+      continue;
+    }
     for (int nt = 0; nt < c.ntiles; ++nt) {
       __half* dst = h.data() + ctx->tc_off[l] + (size_t)nt * taps * 2 * c.nout * 64;
       for (int t = 0; t < taps; ++t)
@@ -406,7 +595,6 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
   TcLayer c;
   XF_REQUIRE(tc_layer_cfg(layer, c) && ctx->d_tcw, "conv_tc: layer %d not prepared for the tensor-core path", layer);
   XF_REQUIRE(out_split || out_f32, "conv_tc: no output");
-  XF_REQUIRE(!(out_split && c.ntiles > 1), "conv_tc: split output needs a single N tile");
   if (g_conv_impl == 2 && kLayers[layer].ks == 3 && kLayers[layer].stride == 1 && c.ntiles == 1 && c.cinp == c.nout)
     return launch_conv_tc_halo(ctx, layer, in_split, B, Hin, Win, out_split, out_f32, st);
   PFN_encodeTiled enc = get_encode_tiled();
@@ -439,12 +627,40 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
   P.pad = sp.ks / 2;
   P.tw_log2 = tw_log2;
   P.out_split = out_split;
-  P.split_c = c.nout;
   P.out_f32 = out_f32;
   P.f32_c = sp.cout;
   P.relu = sp.relu;
   const int n_tiles = cdiv(Ho, TH) * cdiv(Wo, TW) * B;
   const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
+  P.split_c = sp.cout <= 32 ? 32 : sp.cout;   // channel count of the split output tensor [hi(split_c) | lo(split_c)]
+  if (c.cinp == 128) {
+    const cuuint64_t wdims[2] = {64, (cuuint64_t)c.ntiles * taps * 4 * 64};
+    const cuuint64_t wstrides[1] = {128};
+    const cuuint32_t wbox[2] = {64, 256};
+    const cuuint32_t westr[2] = {1, 1};
+    r = enc(&P.wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)((__half*)ctx->d_tcw + ctx->tc_off[layer]), wdims, wstrides, wbox,
+            westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(weights128, layer %d) failed: %d", layer, (int)r);
+      return XF_E_CUDA;
+    }
+    P.bias = ctx->d_weights + ctx->table.b_off[layer];
+    P.f32_co0 = 0;
+    P.n_real = 64;
+    const int gx = cdiv(ctx->sm_count, c.ntiles) < n_tiles ? cdiv(ctx->sm_count, c.ntiles) : n_tiles;
+    dim3 g2(gx, c.ntiles);
+    static bool attr3 = false, attr1 = false;
+    if (sp.ks == 3) {
+      if (!attr3) { XF_CUDA(cudaFuncSetAttribute(conv_tc128_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C128_SMEM)); attr3 = true; }
+      conv_tc128_kernel<3><<<g2, CT_THREADS, C128_SMEM, st>>>(P);
+    } else {
+      if (!attr1) { XF_CUDA(cudaFuncSetAttribute(conv_tc128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C128_SMEM)); attr1 = true; }
+      conv_tc128_kernel<1><<<g2, CT_THREADS, C128_SMEM, st>>>(P);
+    }
+    XF_LAUNCH_CHECK();
+    return XF_OK;
+  }
   for (int nt = 0; nt < c.ntiles; ++nt) {
     const cuuint64_t wdims[2] = {64, (cuuint64_t)taps * 2 * c.nout};
     const cuuint64_t wstrides[1] = {128};
@@ -481,7 +697,7 @@ extern "C" int xfeat_debug_conv_layer_tc(xfeat_ctx* ctx, int layer, const float*
                                          void* d_scratch, size_t scratch_bytes, void* stream) {
   XF_REQUIRE(ctx && d_in && d_out && d_scratch && layer >= 0 && layer < xf::L_COUNT, "debug_conv_layer_tc: bad arguments");
   XF_REQUIRE(xf::conv_tc_eligible(layer), "debug_conv_layer_tc: layer %d has no tensor-core configuration", layer);
-  const int cin = xf::kLayers[layer].cin, cinp = cin <= 32 ? 32 : 64;
+  const int cin = xf::kLayers[layer].cin, cinp = cin <= 32 ? 32 : (cin <= 64 ? 64 : 128);
   const int64_t npix = (int64_t)B * H * W;
   XF_REQUIRE(scratch_bytes >= (size_t)npix * 4 * cinp, "debug_conv_layer_tc: scratch must hold B*H*W*%d bytes", 4 * cinp);
   XF_CUDA(cudaSetDevice(ctx->device));

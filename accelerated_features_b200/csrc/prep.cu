@@ -109,6 +109,58 @@ __global__ void __launch_bounds__(256) gray_identity_f32_kernel(const float* __r
   }
 }
 
+// Fast path for camera-style input: uint8 HWC (3 interleaved channels, e.g. cv2 BGR), already at network resolution.
+// 4 pixels (12 bytes = three aligned 32-bit words) per thread; same arithmetic as the generic kernel:
+// per channel float(u8)/255 (parse_input, xfeat.py:400-401), channel sum, /3 (model.py:135).
+__global__ void __launch_bounds__(256) gray_identity_u8hwc_kernel(const unsigned char* __restrict__ img, int64_t sb, int64_t sh,
+                                                                  int div255, int H, int W4, float* __restrict__ gray,
+                                                                  double* __restrict__ stats) {
+  const int b = blockIdx.z;
+  const int x4 = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const bool in = (x4 < W4) && (y < H);
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (in) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(img + (int64_t)b * sb + (int64_t)y * sh) + 3 * x4;
+    const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    const unsigned char by[12] = {(unsigned char)(w0), (unsigned char)(w0 >> 8), (unsigned char)(w0 >> 16), (unsigned char)(w0 >> 24),
+                                  (unsigned char)(w1), (unsigned char)(w1 >> 8), (unsigned char)(w1 >> 16), (unsigned char)(w1 >> 24),
+                                  (unsigned char)(w2), (unsigned char)(w2 >> 8), (unsigned char)(w2 >> 16), (unsigned char)(w2 >> 24)};
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = (float)by[3 * i + c];
+        if (div255) v = __fdiv_rn(v, 255.f);
+        acc = __fadd_rn(acc, v);
+      }
+      o[i] = __fdiv_rn(acc, 3.f);
+    }
+    g = make_float4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<float4*>(gray + ((int64_t)b * H + y) * (W4 * 4))[x4] = g;
+  }
+  double s = (double)g.x + (double)g.y + (double)g.z + (double)g.w;
+  double ss = (double)g.x * g.x + (double)g.y * g.y + (double)g.z * g.z + (double)g.w * g.w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  __shared__ double sh_s[8], sh_ss[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh_s[warp] = s; sh_ss[warp] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += sh_s[i]; c2 += sh_ss[i]; }
+    atomicAdd(&stats[2 * b], a);
+    atomicAdd(&stats[2 * b + 1], c2);
+  }
+}
+
 // InstanceNorm2d(1): (g - mean) * rsqrt(var_biased + 1e-5), float4 vectorised, in place.
 __global__ void __launch_bounds__(256) instnorm_kernel(float* __restrict__ gray, const double* __restrict__ stats,
                                                        int HW4) {
@@ -185,7 +237,13 @@ extern "C" int xfeat_preprocess(const void* d_img, int dtype, int B, int C, int 
   dim3 grid(xf::cdiv(W, 64), xf::cdiv(H, 4), B);
   const bool fast = dtype == XF_DTYPE_F32 && Hi == H && Wi == W && stride_w == 1 && ((uintptr_t)d_img % 16) == 0 &&
                     stride_b % 4 == 0 && stride_c % 4 == 0 && stride_h % 4 == 0;
-  if (fast) {
+  const bool fast_u8 = dtype == XF_DTYPE_U8 && Hi == H && Wi == W && C == 3 && stride_c == 1 && stride_w == 3 &&
+                       ((uintptr_t)d_img % 4) == 0 && stride_b % 4 == 0 && stride_h % 4 == 0;
+  if (fast_u8) {
+    dim3 g4(xf::cdiv(W / 4, 64), xf::cdiv(H, 4), B);
+    xf::gray_identity_u8hwc_kernel<<<g4, 256, 0, st>>>((const unsigned char*)d_img, stride_b, stride_h, div255, H, W / 4, d_xn,
+                                                       d_stats);
+  } else if (fast) {
     dim3 g4(xf::cdiv(W / 4, 64), xf::cdiv(H, 4), B);
     xf::gray_identity_f32_kernel<<<g4, 256, 0, st>>>((const float*)d_img, C, stride_b, stride_c, stride_h, div255, H, W / 4,
                                                      d_xn, d_stats);

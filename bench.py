@@ -212,14 +212,21 @@ def run_gpu(args):
     rc = torch.empty((BATCH,), dtype=torch.int32).pin_memory()
     main = torch.cuda.current_stream(dev)
 
-    def upload(i):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[i % 2])
-            bufs[i % 2][0].copy_(h1, non_blocking=True)
-            bufs[i % 2][1].copy_(h2, non_blocking=True)
-            ready[i % 2].record(copy_stream)
+    # uint8 HWC images (what cv2 / camera callers hand to match_xfeat): 4x fewer bytes over PCIe, "/255" on the device
+    hu1 = (torch.rand(BATCH, H, W, 3, generator=g) * 255).to(torch.uint8).pin_memory()
+    hu2 = (torch.rand(BATCH, H, W, 3, generator=g) * 255).to(torch.uint8).pin_memory()
+    ubufs = [(torch.empty_like(hu1, device=dev), torch.empty_like(hu2, device=dev)) for _ in range(2)]
 
-    def e2e_run(n):
+    def e2e_run(n, u8=False):
+        src1, src2, bb = (hu1, hu2, ubufs) if u8 else (h1, h2, bufs)
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[i % 2])
+                bb[i % 2][0].copy_(src1, non_blocking=True)
+                bb[i % 2][1].copy_(src2, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
         for ev in freed:
             ev.record(main)
         upload(0)
@@ -227,7 +234,11 @@ def run_gpu(args):
             if i + 1 < n:
                 upload(i + 1)
             main.wait_event(ready[i % 2])
-            mk0, mk1, cnt = xf._match_sparse_batch_device(bufs[i % 2][0], bufs[i % 2][1], TOPK, -1)
+            if u8:
+                mk0, mk1, cnt = xf._match_sparse_batch_device(bb[i % 2][0].permute(0, 3, 1, 2), bb[i % 2][1].permute(0, 3, 1, 2),
+                                                              TOPK, -1, div255=True)
+            else:
+                mk0, mk1, cnt = xf._match_sparse_batch_device(bb[i % 2][0], bb[i % 2][1], TOPK, -1)
             freed[i % 2].record(main)
             r0.copy_(mk0, non_blocking=True)
             r1.copy_(mk1, non_blocking=True)
@@ -241,12 +252,29 @@ def run_gpu(args):
     s1.record()
     barrier()
     e2e_ms = s0.elapsed_time(s1)
+    e2e_run(2, u8=True)
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    e2e_run(args.steps, u8=True)
+    u1.record()
+    barrier()
+    e2e_u8_ms = u0.elapsed_time(u1)
+    # host link alone: the same fp32 upload with no kernels behind it
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        bufs[0][0].copy_(h1, non_blocking=True)
+        bufs[0][1].copy_(h2, non_blocking=True)
+    c1.record()
+    barrier()
+    h2d_gbs = 3 * 2 * h1.numel() * 4 / (c0.elapsed_time(c1) / 1e3) / 1e9
     clocks = sampler.stop() if sampler else None
 
-    t = torch.tensor([ms_total, e2e_ms, mnn_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, mnn_ms, e2e_u8_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, mnn_ms = t.tolist()
+    ms_total, e2e_ms, mnn_ms, e2e_u8_ms = t.tolist()
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -267,7 +295,11 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "pairs_per_gpu": BATCH, "top_k": TOPK, "l2": "inputs 472 MB/step > 126 MB L2",
                        "mean_keypoints": [n1_mean, n2_mean], "mean_matches_per_pair": matches_mean, "parallelism": f"pair-sharded x{world}"},
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * h1.numel() * 4),
-                    "d2h_bytes_per_step": int(2 * r0.numel() * 4 + rc.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(2 * r0.numel() * 4 + rc.numel() * 4), "ms_per_step": e2e_ms / args.steps,
+                    "h2d_only_gbs": h2d_gbs,
+                    "note": "fp32 images (the reference's synthetic input style): bound by the host link, see h2d_only_gbs"},
+            "e2e_u8": {"value": pairs / (e2e_u8_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(2 * hu1.numel()),
+                       "ms_per_step": e2e_u8_ms / args.steps, "input": "uint8 HWC images, /255 on device (camera / cv2 callers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": kname, "bound": "tensor",

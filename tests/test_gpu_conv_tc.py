@@ -42,6 +42,9 @@ CASES = [  # (layer id, oracle prefix, basic layer?, H_in, W_in, pad, stride)
     (7, "block3.0", True, 120, 160, 1, 2), (7, "block3.0", True, 24, 40, 1, 2),
     (10, "block4.0", True, 60, 80, 1, 2), (10, "block4.0", True, 20, 80, 1, 2),
     (13, "block5.0", True, 30, 40, 1, 2), (13, "block5.0", True, 10, 40, 1, 2),
+    # 128 input channels: weights streamed per tap
+    (14, "block5.1", True, 15, 20, 1, 1), (15, "block5.2", True, 5, 7, 1, 1), (16, "block5.3", True, 15, 20, 0, 1),
+    (14, "block5.1", True, 39, 52, 1, 1),
 ]
 
 
@@ -61,7 +64,7 @@ def test_conv_tc_layer_vs_oracle(xf, oracle_state, case):
     Ho, Wo = want.shape[2], want.shape[3]
     xin = x.permute(0, 2, 3, 1).contiguous().cuda()
     out = torch.empty((B, Ho, Wo, cout), device="cuda")
-    scratch = torch.empty(B * H * W * 256, dtype=torch.uint8, device="cuda")
+    scratch = torch.empty(B * H * W * 512, dtype=torch.uint8, device="cuda")
     _lib.check(xf._lib.xfeat_debug_conv_layer_tc(xf._ctx, layer, xin.data_ptr(), B, H, W, out.data_ptr(), scratch.data_ptr(),
                                                  scratch.numel(), torch.cuda.current_stream().cuda_stream), "conv_tc")
     torch.cuda.synchronize()
