@@ -138,6 +138,8 @@ int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split,
 int conv_tc_prepare(xfeat_ctx* ctx);
 int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int H, int W, __half* out_split,
                    float* out_f32, cudaStream_t st);
+int launch_head_chain(const xfeat_ctx* ctx, int mode, const __half* in_split, int B, int Hc, int Wc, float* out, float* logits,
+                      cudaStream_t st);
 int launch_split_nhwc(const float* in, __half* out, int64_t npix, int C, int CP, cudaStream_t st);
 int launch_unfold8_split(const float* xn, __half* out, int B, int Hc, int Wc, cudaStream_t st);
 int launch_stem_chain(const float* h_weights, const LayerTable& t, const float* xn, float* a1, float* a2, float* a3,

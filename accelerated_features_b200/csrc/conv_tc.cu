@@ -493,6 +493,8 @@ static bool tc_layer_cfg(int layer, TcLayer& c) {
   if (s.cin == 24 && s.cout == 64) { c = {32, 64, 1}; return true; }            // block3.0 (stride 2)
   if (s.cin == 64 && s.cout == 128) { c = {64, 64, 2}; return true; }           // block5.0 (stride 2), two N tiles
   if (s.cin == 128 && s.stride == 1) { c = {128, 64, s.cout / 64}; return true; }   // block5.1/5.2 (3x3), block5.3 (1x1): streamed weights
+  if (s.cin == 64 && s.cout == 65) { c = {64, 80, 1}; return true; }            // keypoint_head.3, N padded to 80 (head_chain_tc.cu only)
+  if (s.cin == 64 && s.cout == 1) { c = {64, 16, 1}; return true; }             // heatmap_head.2, N padded to 16 (head_chain_tc.cu only)
   return false;
 }
 bool conv_tc_eligible(int layer) {

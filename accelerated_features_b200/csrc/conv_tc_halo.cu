@@ -18,13 +18,17 @@
 namespace xf {
 
 constexpr int CH_THREADS = 192;
-constexpr int CH_PATCH_BYTES = 34816;   // >= (2*PW + 2 + 128) * 128 for PW <= 66, multiple of 1024
+constexpr int CH_PATCH_BYTES = 34816;   // CINP=32: >= (2*PW + 2 + 128) * 128 for PW <= 66, multiple of 1024
+constexpr int CH_PATCH64_BYTES = 27648; // CINP=64: PW <= 42 (TW <= 40): 214 rows x 128 B, so that THREE buffers fit beside the weights
 
 template <int CINP, int NOUT>
 struct HaloCfg {
   static constexpr int W_GROUP = NOUT * 128;
   static constexpr size_t W_BYTES = (size_t)9 * 2 * W_GROUP;
-  static constexpr size_t SMEM = 1024 + W_BYTES + 2 * (size_t)CH_PATCH_BYTES + 768;
+  // patch buffers: CINP=32 -> 4-deep ring over tiles; CINP=64 -> 3-deep ring over the sequence hi(t), lo(t), hi(t+1), ...
+  static constexpr int NP = (CINP == 32) ? 4 : 3;
+  static constexpr int PB = (CINP == 32) ? CH_PATCH_BYTES : CH_PATCH64_BYTES;
+  static constexpr size_t SMEM = 1024 + W_BYTES + NP * (size_t)PB + 768;
   static constexpr int TMEM_COLS = 2 * NOUT;
 };
 
@@ -54,14 +58,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* sW = base;
-  unsigned char* sP = base + C::W_BYTES;                     // two patch buffers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + C::W_BYTES + 2 * CH_PATCH_BYTES);
+  unsigned char* sP = base + C::W_BYTES;                     // patch buffers
+  constexpr int NP = C::NP;
+  constexpr int PB = C::PB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + C::W_BYTES + NP * PB);
   uint64_t* w_full = bars;
-  uint64_t* p_full = bars + 1;     // [2]
-  uint64_t* p_empty = bars + 3;    // [2]
-  uint64_t* acc_full = bars + 5;   // [2]
-  uint64_t* acc_empty = bars + 7;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* p_full = bars + 1;            // [NP]
+  uint64_t* p_empty = bars + 1 + NP;      // [NP]
+  uint64_t* acc_full = bars + 1 + 2 * NP; // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* sBias = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,9 +81,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
     tc::tma_prefetch_desc(&P.amap);
     tc::tma_prefetch_desc(&P.wmap);
     tc::mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NP; ++i) {
       tc::mbar_init(&p_full[i], 1);
       tc::mbar_init(&p_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc_full[i], 1);
       tc::mbar_init(&acc_empty[i], 4);
     }
@@ -94,7 +102,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
 
   // CINP = 64: buffer 0 = hi patch, buffer 1 = lo patch of the SAME tile (each single-buffered; the hi-only MMAs of a
   //            tile run first so the next tile's hi patch can stream in while the lo MMAs run, and vice versa).
-  // CINP = 32: buffers 0/1 alternate between tiles (rows are [hi(32)|lo(32)]).
+  // CINP = 32: a ring of NP buffers over tiles (rows are [hi(32)|lo(32)]): the producer runs up to NP-1 tiles ahead.
   if (warp == 0) {
     if (lane == 0) {
       tc::mbar_expect_tx(w_full, (uint32_t)C::W_BYTES);
@@ -104,18 +112,19 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
         const int b = tile / tiles_img, rem = tile - b * tiles_img;
         const int y0 = (rem / tiles_x) * P.TH - 1, x0 = (rem % tiles_x) * P.TW - 1;
         if (CINP == 64) {
-          const uint32_t ph = tcount & 1;
-          tc::mbar_wait(&p_empty[0], ph ^ 1);
-          tc::mbar_expect_tx(&p_full[0], patch_tx);
-          tc::tma_load_4d(sP, &P.amap, &p_full[0], 0, x0, y0, b);
-          tc::mbar_wait(&p_empty[1], ph ^ 1);
-          tc::mbar_expect_tx(&p_full[1], patch_tx);
-          tc::tma_load_4d(sP + CH_PATCH_BYTES, &P.amap, &p_full[1], 64, x0, y0, b);
+#pragma unroll
+          for (int term = 0; term < 2; ++term) {       // load index li = 2*tcount + term: hi then lo patch of this tile
+            const uint32_t li = 2 * tcount + term;
+            const int s = li % NP;
+            tc::mbar_wait(&p_empty[s], ((li / NP) & 1) ^ 1);
+            tc::mbar_expect_tx(&p_full[s], patch_tx);
+            tc::tma_load_4d(sP + (size_t)s * PB, &P.amap, &p_full[s], 64 * term, x0, y0, b);
+          }
         } else {
-          const int s = tcount & 1;
-          tc::mbar_wait(&p_empty[s], ((tcount >> 1) & 1) ^ 1);
+          const int s = tcount % NP;
+          tc::mbar_wait(&p_empty[s], ((tcount / NP) & 1) ^ 1);
           tc::mbar_expect_tx(&p_full[s], patch_tx);
-          tc::tma_load_4d(sP + (size_t)s * CH_PATCH_BYTES, &P.amap, &p_full[s], 0, x0, y0, b);
+          tc::tma_load_4d(sP + (size_t)s * PB, &P.amap, &p_full[s], 0, x0, y0, b);
         }
       }
     }
@@ -132,9 +141,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
         tc::tc_fence_after();
         const uint32_t d = tmem + a * NOUT;
         if (CINP == 64) {
-          const uint32_t ph = tcount & 1;
-          const uint32_t hi_base = tc::smem_u32(sP), lo_base = hi_base + CH_PATCH_BYTES;
-          tc::mbar_wait(&p_full[0], ph);
+          const uint32_t li_hi = 2 * tcount, li_lo = 2 * tcount + 1;
+          const int s_hi = li_hi % NP, s_lo = li_lo % NP;
+          const uint32_t hi_base = tc::smem_u32(sP) + (uint32_t)s_hi * PB, lo_base = tc::smem_u32(sP) + (uint32_t)s_lo * PB;
+          tc::mbar_wait(&p_full[s_hi], (li_hi / NP) & 1);
           tc::tc_fence_after();
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * 128u;
@@ -146,8 +156,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
           }
-          tc::umma_commit(&p_empty[0]);            // hi patch may be overwritten once these MMAs retire
-          tc::mbar_wait(&p_full[1], ph);
+          tc::umma_commit(&p_empty[s_hi]);         // hi patch buffer may be refilled once these MMAs retire
+          tc::mbar_wait(&p_full[s_lo], (li_lo / NP) & 1);
           tc::tc_fence_after();
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * 128u;
@@ -156,11 +166,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc::umma_f16(d, alo + 2 * k, whi + 2 * k, idesc, 1u);
           }
-          tc::umma_commit(&p_empty[1]);
+          tc::umma_commit(&p_empty[s_lo]);
         } else {
-          const int s = tcount & 1;
-          const uint32_t p_base = tc::smem_u32(sP) + (uint32_t)s * CH_PATCH_BYTES;
-          tc::mbar_wait(&p_full[s], (tcount >> 1) & 1);
+          const int s = tcount % NP;
+          const uint32_t p_base = tc::smem_u32(sP) + (uint32_t)s * PB;
+          tc::mbar_wait(&p_full[s], (tcount / NP) & 1);
           tc::tc_fence_after();
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * 128u;
@@ -248,10 +258,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
 }
 
 // tile geometry: TW <= 64 (PW <= 66), TH = 128 / PW; minimise MMA rows spent per valid output pixel
-static void pick_halo_tile(int H, int W, int& TW, int& TH) {
+static void pick_halo_tile(int H, int W, int tw_max, int& TW, int& TH) {
   double best = 1e30;
   TW = 16; TH = 7;
-  for (int tw = 8; tw <= 64; ++tw) {
+  for (int tw = 8; tw <= tw_max; ++tw) {
     const int pw = tw + 2, th = 128 / pw;
     if (th < 1) continue;
     const double tiles = (double)cdiv(W, tw) * cdiv(H, th);
@@ -278,7 +288,7 @@ int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split,
     return XF_E_CUDA;
   }
   HaloParams P;
-  pick_halo_tile(H, W, P.TW, P.TH);
+  pick_halo_tile(H, W, c64 ? 40 : 64, P.TW, P.TH);
   P.PW = P.TW + 2;
   const cuuint64_t row_bytes = (cuuint64_t)2 * cinp * sizeof(__half);
   const cuuint64_t dims[4] = {(cuuint64_t)2 * cinp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
