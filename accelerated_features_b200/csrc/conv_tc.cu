@@ -42,7 +42,10 @@ struct ConvTcCfg {
   static constexpr int NS = NS_MAX > 6 ? 6 : NS_MAX;                  // A stages (one tap each)
   static constexpr size_t A_BYTES = (size_t)NS * A_STAGE;
   static constexpr size_t SMEM = 1024 + W_BYTES + A_BYTES + 768;
-  static constexpr int TMEM_COLS = 2 * NOUT < 32 ? 32 : 2 * NOUT;     // two accumulator buffers (power of two >= 32)
+  // accumulator per buffer: columns [0,NOUT) = terms against weight group 0, [NOUT,2*NOUT) = against group 1: a single UMMA
+  // with N = 2*NOUT reads the activation operand once for both groups (the layers are shared-memory-bandwidth bound).
+  static constexpr int ACC_COLS = 2 * NOUT;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;                      // two accumulator buffers
   static_assert(NS >= 2, "need at least two A stages");
   static_assert(CINP == 32 || CINP == 64, "CINP");
   static_assert(NOUT == 32 || NOUT == 64, "NOUT");
@@ -136,13 +139,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);
+      constexpr uint32_t idesc2 = tc::make_idesc(/*F16*/ 0, 128, 2 * NOUT);
       tc::mbar_wait(w_full, 0);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         const int a = tcount & 1;
         tc::mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
         tc::tc_fence_after();
-        const uint32_t d = tmem + a * NOUT;
+        const uint32_t d = tmem + a * C::ACC_COLS;
         for (int tap = 0; tap < C::TAPS; ++tap, ++it) {
           const int s = it % C::NS;
           tc::mbar_wait(&a_full[s], (it / C::NS) & 1);
@@ -150,20 +154,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
           const uint32_t a_addr = tc::smem_u32(sA + (size_t)s * C::A_STAGE);
           const uint32_t w_addr = tc::smem_u32(sW + (size_t)tap * 2 * C::W_GROUP);
           const uint64_t a0 = tc::make_desc_sw128(a_addr, 1024);
-          const uint64_t w0 = tc::make_desc_sw128(w_addr, 1024), w1 = tc::make_desc_sw128(w_addr + C::W_GROUP, 1024);
+          const uint64_t w0 = tc::make_desc_sw128(w_addr, 1024);   // group 0, and (N = 2*NOUT) groups [0 ; 1] stacked
           if (C::A_BOXES == 2) {
             const uint64_t a1 = tc::make_desc_sw128(a_addr + CT_ABOX, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc, (tap | k) ? 1u : 0u);   // hi . whi
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc2, (tap | k) ? 1u : 0u);  // hi.whi | hi.wlo
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w1 + 2 * k, idesc, 1u);                    // hi . wlo
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a1 + 2 * k, w0 + 2 * k, idesc, 1u);                    // lo . whi
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a1 + 2 * k, w0 + 2 * k, idesc, 1u);                    // lo.whi
           } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc, (tap | k) ? 1u : 0u);   // [hi|lo].[whi|whi]
-#pragma unroll
-            for (int k = 0; k < 2; ++k) tc::umma_f16(d, a0 + 2 * k, w1 + 2 * k, idesc, 1u);                    // hi . wlo
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc2, (tap | k) ? 1u : 0u);  // [hi|lo].[[whi|whi];[wlo|0]]
           }
           tc::umma_commit(&a_empty[s]);
         }
@@ -183,12 +183,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
       const int y = (rem / tiles_x) * TH + ph_, x = (rem % tiles_x) * TW + pw_;
       tc::mbar_wait(&acc_full[a], (tcount >> 1) & 1);
       tc::tc_fence_after();
-      uint32_t v[NOUT];
+      uint32_t v[2 * NOUT];
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < NOUT / 32; ++c) {
+      for (int c = 0; c < 2 * NOUT / 32; ++c) {
         uint32_t t[32];
-        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * NOUT + c * 32, t);
+        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * C::ACC_COLS + c * 32, t);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[c * 32 + j] = t[j];
       }
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         float o[NOUT];
 #pragma unroll
         for (int c = 0; c < NOUT; ++c) {
-          float t0 = fmaf(__uint_as_float(v[c]), P.inv_wscale, sBias[c]);
+          float t0 = fmaf(__uint_as_float(v[c]) + __uint_as_float(v[NOUT + c]), P.inv_wscale, sBias[c]);
           if (P.relu) t0 = fmaxf(t0, 0.f);
           o[c] = t0;
         }
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
     tc::fence_barrier_init();
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 128);
+    tc::tmem_alloc(tmem_slot, 256);
     tc::tmem_relinquish();
   }
   tc::tc_fence_before();
@@ -320,12 +320,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);
+      constexpr uint32_t idesc2 = tc::make_idesc(/*F16*/ 0, 128, 2 * NOUT);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
         const int a = tcount & 1;
         tc::mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
         tc::tc_fence_after();
-        const uint32_t d = tmem + a * NOUT;
+        const uint32_t d = tmem + a * 2 * NOUT;
         for (int tap = 0; tap < TAPS; ++tap, ++it) {
           const int s = it % NS;
           tc::mbar_wait(&s_full[s], (it / NS) & 1);
@@ -334,13 +335,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
             const uint64_t ahi = tc::make_desc_sw128(sa + kb * CT_ABOX, 1024), alo = tc::make_desc_sw128(sa + (2 + kb) * CT_ABOX, 1024);
-            const uint64_t whi = tc::make_desc_sw128(sw + (2 * kb) * C128_WBOX, 1024), wlo = tc::make_desc_sw128(sw + (2 * kb + 1) * C128_WBOX, 1024);
+            const uint64_t whi = tc::make_desc_sw128(sw + (2 * kb) * C128_WBOX, 1024);   // also [whi_kb ; wlo_kb] with N = 128
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, whi + 2 * k, idesc, (tap | kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, whi + 2 * k, idesc2, (tap | kb | k) ? 1u : 0u);  // hi.whi | hi.wlo
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, alo + 2 * k, whi + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, alo + 2 * k, whi + 2 * k, idesc, 1u);                         // lo.whi
           }
           tc::umma_commit(&s_empty[s]);
         }
@@ -359,10 +358,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
       const int y = (rem / tiles_x) * TH + ph_, x = (rem % tiles_x) * TW + pw_;
       tc::mbar_wait(&acc_full[a], (tcount >> 1) & 1);
       tc::tc_fence_after();
-      uint32_t v0[32], v1[32];
+      uint32_t v0[32], v1[32], v2[32], v3[32];
       __syncwarp();
-      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * NOUT, v0);
-      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * NOUT + 32, v1);
+      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * 2 * NOUT, v0);
+      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * 2 * NOUT + 32, v1);
+      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * 2 * NOUT + 64, v2);
+      tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * 2 * NOUT + 96, v3);
       tc::tmem_ld_wait();
       tc::tc_fence_before();
       __syncwarp();
@@ -372,8 +373,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
         float o[NOUT];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          float t0 = fmaf(__uint_as_float(v0[c]), P.inv_wscale, sBias[c]);
-          float t1 = fmaf(__uint_as_float(v1[c]), P.inv_wscale, sBias[32 + c]);
+          float t0 = fmaf(__uint_as_float(v0[c]) + __uint_as_float(v2[c]), P.inv_wscale, sBias[c]);
+          float t1 = fmaf(__uint_as_float(v1[c]) + __uint_as_float(v3[c]), P.inv_wscale, sBias[32 + c]);
           if (P.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
           o[c] = t0; o[32 + c] = t1;
         }
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
   __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem, 128);
+    tc::tmem_dealloc(tmem, 256);
   }
 }
 

@@ -29,7 +29,10 @@ struct HaloCfg {
   static constexpr int NP = (CINP == 32) ? 4 : 3;
   static constexpr int PB = (CINP == 32) ? CH_PATCH_BYTES : CH_PATCH64_BYTES;
   static constexpr size_t SMEM = 1024 + W_BYTES + NP * (size_t)PB + 768;
-  static constexpr int TMEM_COLS = 2 * NOUT;
+  // accumulator per buffer: columns [0,NOUT) = terms against whi, [NOUT,2*NOUT) = terms against wlo (one UMMA with
+  // N = 2*NOUT reads the activation operand once for both weight groups); the epilogue adds the two halves.
+  static constexpr int ACC_COLS = 2 * NOUT;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
 };
 
 struct HaloParams {
@@ -131,7 +134,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);
+      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);        // against one weight group
+      constexpr uint32_t idesc2 = tc::make_idesc(/*F16*/ 0, 128, 2 * NOUT);   // against [group0 ; group1] stacked along N
       tc::mbar_wait(w_full, 0);
       const uint32_t w_base = tc::smem_u32(sW);
       uint32_t tcount = 0;
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
         const int a = tcount & 1;
         tc::mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
         tc::tc_fence_after();
-        const uint32_t d = tmem + a * NOUT;
+        const uint32_t d = tmem + a * C::ACC_COLS;
         if (CINP == 64) {
           const uint32_t li_hi = 2 * tcount, li_lo = 2 * tcount + 1;
           const int s_hi = li_hi % NP, s_lo = li_lo % NP;
@@ -149,12 +153,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * 128u;
             const uint64_t ahi = make_desc_sw128_at(hi_base + shift, 1024, P.desc_mode);
-            const uint64_t whi = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2) * C::W_GROUP, 1024);
-            const uint64_t wlo = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2 + 1) * C::W_GROUP, 1024);
+            const uint64_t wboth = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2) * C::W_GROUP, 1024);   // [whi ; wlo], N = 128
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, whi + 2 * k, idesc, (tap | k) ? 1u : 0u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, wboth + 2 * k, idesc2, (tap | k) ? 1u : 0u);   // hi.whi | hi.wlo
           }
           tc::umma_commit(&p_empty[s_hi]);         // hi patch buffer may be refilled once these MMAs retire
           tc::mbar_wait(&p_full[s_lo], (li_lo / NP) & 1);
@@ -175,12 +176,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
           for (int tap = 0; tap < 9; ++tap) {
             const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * 128u;
             const uint64_t a0 = make_desc_sw128_at(p_base + shift, 1024, P.desc_mode);
-            const uint64_t w0 = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2) * C::W_GROUP, 1024);
-            const uint64_t w1 = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2 + 1) * C::W_GROUP, 1024);
+            const uint64_t wboth = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2) * C::W_GROUP, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc, (tap | k) ? 1u : 0u);   // [hi|lo].[whi|whi]
-#pragma unroll
-            for (int k = 0; k < 2; ++k) tc::umma_f16(d, a0 + 2 * k, w1 + 2 * k, idesc, 1u);                    // hi . wlo
+            for (int k = 0; k < 4; ++k)   // [hi|lo] . [[whi|whi] ; [wlo|0]]  ->  cols [0,32): hi.whi + lo.whi, cols [32,64): hi.wlo
+              tc::umma_f16(d, a0 + 2 * k, wboth + 2 * k, idesc2, (tap | k) ? 1u : 0u);
           }
           tc::umma_commit(&p_empty[s]);
         }
@@ -200,12 +199,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
       const int y = (rem / tiles_x) * P.TH + mh, x = (rem % tiles_x) * P.TW + mw;
       tc::mbar_wait(&acc_full[a], (tcount >> 1) & 1);
       tc::tc_fence_after();
-      uint32_t v[NOUT];
+      uint32_t v[2 * NOUT];
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < NOUT / 32; ++c) {
+      for (int c = 0; c < 2 * NOUT / 32; ++c) {
         uint32_t t[32];
-        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * NOUT + c * 32, t);
+        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * C::ACC_COLS + c * 32, t);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[c * 32 + j] = t[j];
       }
@@ -218,7 +217,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
         float o[NOUT];
 #pragma unroll
         for (int c = 0; c < NOUT; ++c) {
-          float t0 = fmaf(__uint_as_float(v[c]), P.inv_wscale, sBias[c]);
+          float t0 = fmaf(__uint_as_float(v[c]) + __uint_as_float(v[NOUT + c]), P.inv_wscale, sBias[c]);
           if (P.relu) t0 = fmaxf(t0, 0.f);
           o[c] = t0;
         }

@@ -7,12 +7,19 @@
 // Everything stays on the device with fixed-capacity buffers; the only host-visible scalars are the per-image counts.
 #include <cub/device/device_segmented_sort.cuh>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace xf {
 
 constexpr int NMS_TX = 64, NMS_TY = 16, NMS_R = 2;
+constexpr int NMS_RW = NMS_TX / 8 + 4, NMS_RH = NMS_TY / 8 + 3;   // cached window of the 1/8-res reliability map
 
+// Phase A: every pixel tests "is 5x5 maximum and > threshold" (separable max in shared memory) and the few hits are
+// compacted into a CTA-local list.  Phase B: the list is scored densely (one candidate per thread) -- the score path
+// (coordinate arithmetic, nearest + bilinear sampling) is ~10x longer than the test and would otherwise be executed by
+// every warp under divergence.  Phase C: one global atomic per CTA reserves the output range.
 __global__ void __launch_bounds__(256) nms_score_kernel(const float* __restrict__ heat, const float* __restrict__ rel,
                                                         int H, int W, int Hm, int Wm, float thr, int cap,
                                                         unsigned long long* __restrict__ keys,
@@ -20,12 +27,21 @@ __global__ void __launch_bounds__(256) nms_score_kernel(const float* __restrict_
   __shared__ float sIn[NMS_TY + 2 * NMS_R][NMS_TX + 2 * NMS_R];
   __shared__ float sRow[NMS_TY + 2 * NMS_R][NMS_TX];
   __shared__ unsigned long long sKeys[NMS_TX * NMS_TY];
+  __shared__ unsigned short sCand[NMS_TX * NMS_TY];   // tile-local pixel index of each maximum
   __shared__ int sCnt[3];  // [0] maxima above threshold, [1] kept (score > 0), [2] global base
+  __shared__ float sRel[NMS_RH][NMS_RW];
   const int b = blockIdx.z;
   const int ox0 = blockIdx.x * NMS_TX, oy0 = blockIdx.y * NMS_TY;
   const float* hb = heat + (int64_t)b * H * W;
+  const float* rb = rel + (int64_t)b * Hm * Wm;
+  const int rx0 = ox0 / 8 - 1, ry0 = oy0 / 8 - 1;   // window origin (cells); all bilinear taps of this tile fall inside
   constexpr int PW = NMS_TX + 2 * NMS_R, PH = NMS_TY + 2 * NMS_R;
   if (threadIdx.x < 3) sCnt[threadIdx.x] = 0;
+  for (int idx = threadIdx.x; idx < NMS_RW * NMS_RH; idx += 256) {
+    const int r = idx / NMS_RW, c = idx - r * NMS_RW;
+    const int cy = ry0 + r, cx = rx0 + c;
+    sRel[r][c] = (cy >= 0 && cy < Hm && cx >= 0 && cx < Wm) ? __ldg(rb + (int64_t)cy * Wm + cx) : 0.f;
+  }
   for (int idx = threadIdx.x; idx < PW * PH; idx += 256) {
     const int r = idx / PW, c = idx - r * PW;
     const int y = oy0 - NMS_R + r, x = ox0 - NMS_R + c;
@@ -41,19 +57,37 @@ __global__ void __launch_bounds__(256) nms_score_kernel(const float* __restrict_
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  // ---- phase A: detect + compact ----
 #pragma unroll
   for (int k = 0; k < (NMS_TX * NMS_TY) / 256; ++k) {
     const int idx = threadIdx.x + 256 * k;
     const int r = idx / NMS_TX, c = idx - r * NMS_TX;
-    const int x = ox0 + c, y = oy0 + r;
     float m = sRow[r][c];
 #pragma unroll
     for (int d = 1; d <= 2 * NMS_R; ++d) m = fmaxf(m, sRow[r + d][c]);
     const float v = sIn[r + NMS_R][c + NMS_R];
-    const bool pos = (x < W) && (y < H) && (v == m) && (v > thr);
+    const bool pos = (ox0 + c < W) && (oy0 + r < H) && (v == m) && (v > thr);
+    const unsigned mpos = __ballot_sync(0xffffffffu, pos);
+    if (mpos) {
+      const int leader = __ffs(mpos) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&sCnt[0], __popc(mpos));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (pos) sCand[base + __popc(mpos & ((1u << lane) - 1u))] = (unsigned short)idx;
+    }
+  }
+  __syncthreads();
+  // ---- phase B: score the candidates densely ----
+  const int nc = sCnt[0];
+  for (int i0 = 0; i0 < nc; i0 += 256) {
+    const int i = i0 + threadIdx.x;
     bool keep = false;
     unsigned long long key = 0;
-    if (pos) {
+    if (i < nc) {
+      const int idx = sCand[i];
+      const int r = idx / NMS_TX, c = idx - r * NMS_TX;
+      const int x = ox0 + c, y = oy0 + r;
+      const float v = sIn[r + NMS_R][c + NMS_R];
       // nearest sample of the heat-map at the keypoint itself: round-half-even of x*W/(W-1)-0.5 is x except on the
       // last row/column, where it falls out of bounds -> 0 (reference quirk).
       const int xn = (int)rintf(sparse_src_coord(x, W, W));
@@ -66,23 +100,24 @@ __global__ void __launch_bounds__(256) nms_score_kernel(const float* __restrict_
       const int x0 = (int)fx, y0 = (int)fy;
       const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
       const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
-      const float* rb = rel + (int64_t)b * Hm * Wm;
       float bil = 0.f;
       const bool xin0 = (x0 >= 0 && x0 < Wm), xin1 = (x0 + 1 >= 0 && x0 + 1 < Wm);
       const bool yin0 = (y0 >= 0 && y0 < Hm), yin1 = (y0 + 1 >= 0 && y0 + 1 < Hm);
-      if (xin0 && yin0) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)y0 * Wm + x0), __fmul_rn(wx0, wy0)));
-      if (xin1 && yin0) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)y0 * Wm + x0 + 1), __fmul_rn(wx1, wy0)));
-      if (xin0 && yin1) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)(y0 + 1) * Wm + x0), __fmul_rn(wx0, wy1)));
-      if (xin1 && yin1) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)(y0 + 1) * Wm + x0 + 1), __fmul_rn(wx1, wy1)));
+      const int wx = x0 - rx0, wy = y0 - ry0;          // position inside the cached window
+      const bool cached = (wx >= 0 && wx + 1 < NMS_RW && wy >= 0 && wy + 1 < NMS_RH);
+      auto R = [&](int yy, int xx) -> float {
+        return cached ? sRel[yy - ry0][xx - rx0] : __ldg(rb + (int64_t)yy * Wm + xx);
+      };
+      if (xin0 && yin0) bil = __fadd_rn(bil, __fmul_rn(R(y0, x0), __fmul_rn(wx0, wy0)));
+      if (xin1 && yin0) bil = __fadd_rn(bil, __fmul_rn(R(y0, x0 + 1), __fmul_rn(wx1, wy0)));
+      if (xin0 && yin1) bil = __fadd_rn(bil, __fmul_rn(R(y0 + 1, x0), __fmul_rn(wx0, wy1)));
+      if (xin1 && yin1) bil = __fadd_rn(bil, __fmul_rn(R(y0 + 1, x0 + 1), __fmul_rn(wx1, wy1)));
       float score = __fmul_rn(kv, bil);
       if (x == 0 && y == 0) score = -1.f;  // indistinguishable from the zero padding rows (xfeat.py:80)
       keep = score > 0.f;                  // `valid = scores > 0` (xfeat.py:98) applied early: positives sort first anyway
       key = ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(y * W + x));
     }
-    // warp-aggregated append into the CTA-local list (shared-memory atomics), one global atomic per CTA below
-    const unsigned mpos = __ballot_sync(0xffffffffu, pos);
     const unsigned mkeep = __ballot_sync(0xffffffffu, keep);
-    if (mpos && lane == 0) atomicAdd(&sCnt[0], __popc(mpos));
     if (mkeep) {
       const int leader = __ffs(mkeep) - 1;
       int base = 0;
@@ -92,9 +127,10 @@ __global__ void __launch_bounds__(256) nms_score_kernel(const float* __restrict_
     }
   }
   __syncthreads();
+  // ---- phase C: reserve the output range, write ----
   const int nk = sCnt[1];
   if (threadIdx.x == 0) {
-    if (sCnt[0]) atomicAdd(&n_cand[b], sCnt[0]);
+    if (nc) atomicAdd(&n_cand[b], nc);
     sCnt[2] = nk ? atomicAdd(&n_keep[b], nk) : 0;
   }
   __syncthreads();
@@ -121,7 +157,8 @@ __device__ __forceinline__ float cubic2(float x) {  // 1 < |x| < 2 (ATen cubic_c
   return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
 }
 
-// den[p] = max(||feats[p]||_2, 1e-12): the denominator of F.normalize(M1, dim=1) (xfeat.py:70). 8 lanes per pixel.
+// den[p] = 1 / max(||feats[p]||_2, 1e-12): reciprocal of the denominator of F.normalize(M1, dim=1) (xfeat.py:70), so that the
+// sampler multiplies instead of dividing 64 times per keypoint (<= 1 ulp away from x / den). 8 lanes per pixel.
 __global__ void __launch_bounds__(256) feat_norm_kernel(const float* __restrict__ feats, float* __restrict__ den,
                                                         int64_t npix) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,10 +173,44 @@ __global__ void __launch_bounds__(256) feat_norm_kernel(const float* __restrict_
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 4);
-  if (pix < npix && sub == 0) den[pix] = fmaxf(sqrtf(s), 1e-12f);
+  if (pix < npix && sub == 0) den[pix] = __fdiv_rn(1.0f, fmaxf(sqrtf(s), 1e-12f));
+}
+
+// Bicubic sample (ATen grid_sampler_2d, A = -0.75, zeros padding) of the channel-normalised map at pixel (x, y), for the 4
+// channels owned by lane l16 of a 16-lane group; returns the un-normalised 4-vector and the group-wide sum of squares.
+__device__ __forceinline__ float4 bicubic4(const float* __restrict__ fb, const float* __restrict__ db, int x, int y, int H, int W,
+                                           int Hm, int Wm, int l16) {
+  const float ix = sparse_src_coord(x, W, Wm), iy = sparse_src_coord(y, H, Hm);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const float tx = __fsub_rn(ix, fx), ty = __fsub_rn(iy, fy);
+  const int x0 = (int)fx - 1, y0 = (int)fy - 1;
+  const float cx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2((1.f - tx) + 1.f)};
+  const float cy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2((1.f - ty) + 1.f)};
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int yy = y0 + i;
+    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xx = x0 + j;
+      if (yy >= 0 && yy < Hm && xx >= 0 && xx < Wm) {  // zeros padding
+        const int64_t p = (int64_t)yy * Wm + xx;
+        float4 v = __ldg(reinterpret_cast<const float4*>(fb + p * 64) + l16);
+        const float d = __ldg(db + p);                 // 1 / F.normalize(M1, dim=1) denominator, xfeat.py:70
+        v.x *= d; v.y *= d; v.z *= d; v.w *= d;
+        rr.x = fmaf(v.x, cx[j], rr.x); rr.y = fmaf(v.y, cx[j], rr.y);
+        rr.z = fmaf(v.z, cx[j], rr.z); rr.w = fmaf(v.w, cx[j], rr.w);
+      }
+    }
+    o.x = fmaf(rr.x, cy[i], o.x); o.y = fmaf(rr.y, cy[i], o.y);
+    o.z = fmaf(rr.z, cy[i], o.z); o.w = fmaf(rr.w, cy[i], o.w);
+  }
+  return o;
 }
 
 // Half a warp per output slot (b, r): lane owns 4 channels. feats: (B,Hm,Wm,64) NHWC un-normalised, den: (B,Hm,Wm).
+// Generic kernel (any top_k): slots are visited in score order, so taps of neighbouring keypoints rarely share L1 lines.
 __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long long* __restrict__ sorted,
                                                           const int* __restrict__ n_keep, const float* __restrict__ feats,
                                                           const float* __restrict__ den, int B, int H, int W, int Hm, int Wm,
@@ -162,33 +233,7 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
     key = sorted[(int64_t)b * cap + r];
     const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
     x = (int)(lin % (uint32_t)W); y = (int)(lin / (uint32_t)W);
-    const float ix = sparse_src_coord(x, W, Wm), iy = sparse_src_coord(y, H, Hm);
-    const float fx = floorf(ix), fy = floorf(iy);
-    const float tx = __fsub_rn(ix, fx), ty = __fsub_rn(iy, fy);
-    const int x0 = (int)fx - 1, y0 = (int)fy - 1;
-    const float cx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2((1.f - tx) + 1.f)};
-    const float cy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2((1.f - ty) + 1.f)};
-    const float* fb = feats + (int64_t)b * Hm * Wm * 64;
-    const float* db = den + (int64_t)b * Hm * Wm;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int yy = y0 + i;
-      float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int xx = x0 + j;
-        if (yy >= 0 && yy < Hm && xx >= 0 && xx < Wm) {  // zeros padding
-          const int64_t p = (int64_t)yy * Wm + xx;
-          float4 v = __ldg(reinterpret_cast<const float4*>(fb + p * 64) + l16);
-          const float d = __ldg(db + p);
-          v.x = __fdiv_rn(v.x, d); v.y = __fdiv_rn(v.y, d); v.z = __fdiv_rn(v.z, d); v.w = __fdiv_rn(v.w, d);
-          rr.x = fmaf(v.x, cx[j], rr.x); rr.y = fmaf(v.y, cx[j], rr.y);
-          rr.z = fmaf(v.z, cx[j], rr.z); rr.w = fmaf(v.w, cx[j], rr.w);
-        }
-      }
-      o.x = fmaf(rr.x, cy[i], o.x); o.y = fmaf(rr.y, cy[i], o.y);
-      o.z = fmaf(rr.z, cy[i], o.z); o.w = fmaf(rr.w, cy[i], o.w);
-    }
+    o = bicubic4(feats + (int64_t)b * Hm * Wm * 64, den + (int64_t)b * Hm * Wm, x, y, H, W, Hm, Wm, l16);
   }
   float ss = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
 #pragma unroll
@@ -203,13 +248,96 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
     }
     return;
   }
-  const float dn = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize(feats, dim=-1), xfeat.py:93
-  *dp = make_float4(__fdiv_rn(o.x, dn), __fdiv_rn(o.y, dn), __fdiv_rn(o.z, dn), __fdiv_rn(o.w, dn));
+  const float dn = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));  // F.normalize(feats, dim=-1), xfeat.py:93
+  *dp = make_float4(o.x * dn, o.y * dn, o.z * dn, o.w * dn);
   if (l16 == 0) {
     kpts[slot * 2] = __fmul_rn((float)x, rw);  // mkpts * [rw, rh], xfeat.py:96
     kpts[slot * 2 + 1] = __fmul_rn((float)y, rh);
     scores[slot] = ord2f((uint32_t)(key >> 32));
     if (kpts_int) { kpts_int[slot * 2] = x; kpts_int[slot * 2 + 1] = y; }
+  }
+}
+
+// One CTA per image (top_k <= SAMPLE_MAX_K): the image's top-k keys are bucketed by feature-map row in shared memory and
+// the keypoints are then processed in that (spatial) order, so the 4x4x256 B tap blocks of neighbouring keypoints hit
+// L1 instead of L2 (5x5 NMS puts keypoints >= 3 px apart while a feature cell covers 8 px).  Results go to the slot given
+// by the score rank, exactly as in the generic kernel.
+constexpr int SAMPLE_MAX_K = 8192, SAMPLE_THREADS = 1024, SAMPLE_MAX_ROWS = 512;
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
+    const unsigned long long* __restrict__ sorted, const int* __restrict__ n_keep, const float* __restrict__ feats,
+    const float* __restrict__ den, int H, int W, int Hm, int Wm, int cap, int top_k, float rw, float rh, float* __restrict__ kpts,
+    float* __restrict__ scores, float* __restrict__ desc, int* __restrict__ n_valid, int* __restrict__ kpts_int) {
+  extern __shared__ unsigned char sm_raw[];
+  unsigned long long* sKey = reinterpret_cast<unsigned long long*>(sm_raw);           // [top_k]
+  unsigned short* sOrder = reinterpret_cast<unsigned short*>(sKey + top_k);            // [top_k]
+  __shared__ int sHist[SAMPLE_MAX_ROWS];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int nv = min(min(n_keep[b], cap), top_k);
+  if (tid == 0) n_valid[b] = nv;
+  for (int i = tid; i < SAMPLE_MAX_ROWS; i += SAMPLE_THREADS) sHist[i] = 0;
+  __syncthreads();
+  for (int r = tid; r < nv; r += SAMPLE_THREADS) {
+    const unsigned long long key = sorted[(int64_t)b * cap + r];
+    sKey[r] = key;
+    const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
+    atomicAdd(&sHist[min((int)(lin / (uint32_t)W) >> 3, SAMPLE_MAX_ROWS - 1)], 1);
+  }
+  __syncthreads();
+  if (tid < 32) {   // exclusive scan of the row histogram (<= 512 buckets) by one warp
+    int carry = 0;
+    for (int i0 = 0; i0 < SAMPLE_MAX_ROWS; i0 += 32) {
+      const int v = sHist[i0 + tid];
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (tid >= o) inc += t;
+      }
+      sHist[i0 + tid] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  for (int r = tid; r < nv; r += SAMPLE_THREADS) {
+    const uint32_t lin = 0xffffffffu - (uint32_t)(sKey[r] & 0xffffffffu);
+    const int pos = atomicAdd(&sHist[min((int)(lin / (uint32_t)W) >> 3, SAMPLE_MAX_ROWS - 1)], 1);
+    sOrder[pos] = (unsigned short)r;
+  }
+  __syncthreads();
+  const int l16 = tid & 15, grp = tid >> 4, ngrp = SAMPLE_THREADS / 16;
+  const float* fb = feats + (int64_t)b * Hm * Wm * 64;
+  const float* db = den + (int64_t)b * Hm * Wm;
+  for (int i = grp; i < ((nv + 1) & ~1); i += ngrp) {   // both half-warps of a warp iterate together (shuffles below)
+    const bool valid = i < nv;
+    const int r = valid ? (int)sOrder[i] : 0;
+    const unsigned long long key = sKey[valid ? r : 0];
+    const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
+    const int x = (int)(lin % (uint32_t)W), y = (int)(lin / (uint32_t)W);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) o = bicubic4(fb, db, x, y, H, W, Hm, Wm, l16);
+    float ss = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
+#pragma unroll
+    for (int s = 8; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    if (valid) {
+      const int64_t slot = (int64_t)b * top_k + r;
+      const float dn = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));  // F.normalize(feats, dim=-1), xfeat.py:93
+      reinterpret_cast<float4*>(desc + slot * 64)[l16] = make_float4(o.x * dn, o.y * dn, o.z * dn, o.w * dn);
+      if (l16 == 0) {
+        kpts[slot * 2] = __fmul_rn((float)x, rw);  // mkpts * [rw, rh], xfeat.py:96
+        kpts[slot * 2 + 1] = __fmul_rn((float)y, rh);
+        scores[slot] = ord2f((uint32_t)(key >> 32));
+        if (kpts_int) { kpts_int[slot * 2] = x; kpts_int[slot * 2 + 1] = y; }
+      }
+    }
+  }
+  // zero-fill the slots past n_valid
+  for (int64_t e = (int64_t)nv * 16 + tid; e < (int64_t)top_k * 16; e += SAMPLE_THREADS) {
+    const int64_t slot = (int64_t)b * top_k + (e >> 4);
+    reinterpret_cast<float4*>(desc + slot * 64)[e & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((e & 15) == 0) {
+      kpts[slot * 2] = 0.f; kpts[slot * 2 + 1] = 0.f; scores[slot] = 0.f;
+      if (kpts_int) { kpts_int[slot * 2] = 0; kpts_int[slot * 2 + 1] = 0; }
+    }
   }
 }
 
@@ -289,10 +417,23 @@ extern "C" int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const f
   const int64_t npix = (int64_t)B * Hm * Wm;
   xf::feat_norm_kernel<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, st>>>(d_feats, ws.den, npix);
   XF_LAUNCH_CHECK();
-  const int64_t slots = (int64_t)B * top_k;
-  xf::sample_desc_kernel<<<(unsigned)((slots * 16 + 255) / 256), 256, 0, st>>>(
-      ws.sorted, ws.n_keep, d_feats, ws.den, B, H, W, Hm, Wm, cap, top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid,
-      d_kpts_int);
+  static const bool use_sorted = getenv("XFEAT_SAMPLE_SORTED") != nullptr;   // experiment knob (default: generic kernel)
+  if (use_sorted && top_k <= xf::SAMPLE_MAX_K && Hm <= xf::SAMPLE_MAX_ROWS) {
+    const size_t smem = (size_t)top_k * (sizeof(unsigned long long) + sizeof(unsigned short));
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      XF_CUDA(cudaFuncSetAttribute(xf::sample_desc_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    xf::sample_desc_sorted_kernel<<<B, xf::SAMPLE_THREADS, smem, st>>>(ws.sorted, ws.n_keep, d_feats, ws.den, H, W, Hm, Wm, cap,
+                                                                      top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid,
+                                                                      d_kpts_int);
+  } else {
+    const int64_t slots = (int64_t)B * top_k;
+    xf::sample_desc_kernel<<<(unsigned)((slots * 16 + 255) / 256), 256, 0, st>>>(
+        ws.sorted, ws.n_keep, d_feats, ws.den, B, H, W, Hm, Wm, cap, top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid,
+        d_kpts_int);
+  }
   XF_LAUNCH_CHECK();
   if (d_n_cand) XF_CUDA(cudaMemcpyAsync(d_n_cand, ws.n_cand, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));
   return XF_OK;

@@ -150,7 +150,8 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    xf = XFeat(top_k=TOPK, device=local)
+    from accelerated_features_b200 import weights as _w
+    xf = XFeat(weights=_w.load_state_dict(_w.DEFAULT_WEIGHTS), top_k=TOPK, device=local)   # dict: no 'loading weights' print on stdout
     lib = _lib.load()
 
     # synthetic data: the reference's own style (minimal_example.py: torch.randn), one distinct shard per rank
