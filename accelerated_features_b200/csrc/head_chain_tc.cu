@@ -49,9 +49,9 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;      // [2]  TMA -> MMA (layer-0 operand of a tile)
   uint64_t* a_free = bars + 3;      // [2]  MMA -> TMA (all GEMMs of the tile that used this buffer have retired)
-  uint64_t* acc_full = bars + 5;    //      MMA -> epilogue, once per GEMM
-  uint64_t* a_ready = bars + 6;     //      epilogue -> MMA: next operand written / accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* acc_full = bars + 5;    // [2]  MMA -> epilogue, once per GEMM of the slot
+  uint64_t* a_ready = bars + 7;     // [2]  epilogue -> MMA: next operand written / accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   float* sBias = reinterpret_cast<float*>(tmem_slot + 2);     // [NH][64] + [NF]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,13 +65,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&a_full[i], 1);
       tc::mbar_init(&a_free[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&a_ready[i], 4);
     }
-    tc::mbar_init(acc_full, 1);
-    tc::mbar_init(a_ready, 4);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 128);
+    tc::tmem_alloc(tmem_slot, 256);   // two slots x 128 columns
     tc::tmem_relinquish();
   }
   tc::tc_fence_before();
@@ -100,28 +100,34 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
       constexpr uint32_t idesc_h = tc::make_idesc(0, 128, 64);
       constexpr uint32_t idesc_f = tc::make_idesc(0, 128, NF);
       tc::mbar_wait(w_full, 0);
-      uint32_t tcount = 0, g = 0;   // g = global GEMM counter
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        const int s = tcount & 1;
-        const uint32_t a_addr = tc::smem_u32(sA + (size_t)s * 2 * HC_ABOX);
-        const uint64_t ahi = tc::make_desc_sw128(a_addr, 1024), alo = tc::make_desc_sw128(a_addr + HC_ABOX, 1024);
-        tc::mbar_wait(&a_full[s], (tcount >> 1) & 1);
-        for (int l = 0; l <= NH; ++l, ++g) {
-          if (g > 0) tc::mbar_wait(a_ready, (g - 1) & 1);    // operand of this layer is in smem, accumulator is drained
-          tc::tc_fence_after();
-          const bool fin = (l == NH);
-          const uint32_t w_addr = fin ? tc::smem_u32(sWf) : tc::smem_u32(sW + (size_t)l * 2 * HC_WBOX);
-          const uint64_t whi = tc::make_desc_sw128(w_addr, 1024);
-          const uint64_t wlo = tc::make_desc_sw128(w_addr + (fin ? WF_GROUP : HC_WBOX), 1024);
-          const uint32_t idesc = fin ? idesc_f : idesc_h;
+      // Two tiles (slots 0/1) are in flight: while the epilogue warps turn slot s's accumulator into the next operand,
+      // the tensor core runs the other slot's GEMM.  g[s] counts the GEMMs issued for slot s.
+      const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      uint32_t g[2] = {0, 0};
+      for (int i0 = 0; i0 < my_tiles; i0 += 2) {
+        const int ns = (i0 + 1 < my_tiles) ? 2 : 1;
+        for (int s = 0; s < ns; ++s) tc::mbar_wait(&a_full[s], ((i0 >> 1)) & 1);
+        for (int l = 0; l <= NH; ++l) {
+          for (int s = 0; s < ns; g[s] += 1, ++s) {
+            const uint32_t a_addr = tc::smem_u32(sA + (size_t)s * 2 * HC_ABOX);
+            const uint64_t ahi = tc::make_desc_sw128(a_addr, 1024), alo = tc::make_desc_sw128(a_addr + HC_ABOX, 1024);
+            if (g[s] > 0) tc::mbar_wait(&a_ready[s], (g[s] - 1) & 1);   // operand in smem, accumulator drained
+            tc::tc_fence_after();
+            const bool fin = (l == NH);
+            const uint32_t w_addr = fin ? tc::smem_u32(sWf) : tc::smem_u32(sW + (size_t)l * 2 * HC_WBOX);
+            const uint64_t whi = tc::make_desc_sw128(w_addr, 1024);
+            const uint64_t wlo = tc::make_desc_sw128(w_addr + (fin ? WF_GROUP : HC_WBOX), 1024);
+            const uint32_t idesc = fin ? idesc_f : idesc_h;
+            const uint32_t d = tmem + s * 128;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::umma_f16(tmem, ahi + 2 * k, whi + 2 * k, idesc, k ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, whi + 2 * k, idesc, k ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::umma_f16(tmem, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc::umma_f16(tmem, alo + 2 * k, whi + 2 * k, idesc, 1u);
-          if (fin) tc::umma_commit(&a_free[s]);              // last reader of this A buffer
-          tc::umma_commit(acc_full);
+            for (int k = 0; k < 4; ++k) tc::umma_f16(d, alo + 2 * k, whi + 2 * k, idesc, 1u);
+            if (fin) tc::umma_commit(&a_free[s]);              // last reader of this A buffer
+            tc::umma_commit(&acc_full[s]);
+          }
         }
       }
     }
@@ -129,15 +135,20 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;                             // pixel row of the tile = TMEM lane
-    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t tcount = 0, g = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-      const int s = tcount & 1;
-      unsigned char* a_hi = sA + (size_t)s * 2 * HC_ABOX;
-      unsigned char* a_lo = a_hi + HC_ABOX;
-      const int64_t pix = (int64_t)tile * 128 + r;
-      for (int l = 0; l <= NH; ++l, ++g) {
-        tc::mbar_wait(acc_full, g & 1);
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    uint32_t g[2] = {0, 0};
+    for (int i0 = 0; i0 < my_tiles; i0 += 2) {
+      const int ns = (i0 + 1 < my_tiles) ? 2 : 1;
+     for (int l = 0; l <= NH; ++l) {
+      for (int s = 0; s < ns; g[s] += 1, ++s) {
+        const int tile = (int)blockIdx.x + (i0 + s) * (int)gridDim.x;
+        unsigned char* a_hi = sA + (size_t)s * 2 * HC_ABOX;
+        unsigned char* a_lo = a_hi + HC_ABOX;
+        const int64_t pix = (int64_t)tile * 128 + r;
+        const uint32_t lane_addr = lane_base + s * 128;
+        uint64_t* const a_ready_s = &a_ready[s];
+        tc::mbar_wait(&acc_full[s], g[s] & 1);
         tc::tc_fence_after();
         if (l < NH) {
           // ---- hidden layer: bias + ReLU, re-split, write the next A operand (128B swizzle: chunk j of row r at j ^ (r & 7)) ----
@@ -169,7 +180,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
           tc::fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core (async proxy)
           tc::tc_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(a_ready);
+          if (lane == 0) tc::mbar_arrive(a_ready_s);
         } else if (MODE == 0) {
           // ---- keypoint logits: soft-max over 65, drop the dustbin, 8x8 depth-to-space (xfeat.py:242-247) ----
           uint32_t v0[32], v1[32], v2[32];
@@ -180,7 +191,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
           tc::tmem_ld_wait();
           tc::tc_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(a_ready);  // accumulator drained: the next tile's first GEMM may start
+          if (lane == 0) tc::mbar_arrive(a_ready_s);  // accumulator drained: this slot's next tile may start
           if (pix < P.npix) {
             const float inv = P.inv_ws_fin;
             const float* bs = sBias + NH * 64;
@@ -227,20 +238,21 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
           tc::tmem_ld_wait();
           tc::tc_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(a_ready);
+          if (lane == 0) tc::mbar_arrive(a_ready_s);
           if (pix < P.npix) {
             const float zz = fmaf(__uint_as_float(v0[0]), P.inv_ws_fin, sBias[NH * 64]);
             P.out[pix] = 1.0f / (1.0f + expf(-zz));
           }
         }
       }
+     }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem, 128);
+    tc::tmem_dealloc(tmem, 256);
   }
 }
 
