@@ -137,13 +137,13 @@ int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split,
                         float* out_f32, cudaStream_t st);
 int conv_tc_prepare(xfeat_ctx* ctx);
 int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int H, int W, __half* out_split,
-                   float* out_f32, cudaStream_t st);
+                   float* out_f32, cudaStream_t st, const float* skip_xn = nullptr);
 int launch_head_chain(const xfeat_ctx* ctx, int mode, const __half* in_split, int B, int Hc, int Wc, float* out, float* logits,
                       cudaStream_t st);
 int launch_split_nhwc(const float* in, __half* out, int64_t npix, int C, int CP, cudaStream_t st);
 int launch_unfold8_split(const float* xn, __half* out, int B, int Hc, int Wc, cudaStream_t st);
 int launch_stem_chain(const float* h_weights, const LayerTable& t, const float* xn, float* a1, float* a2, float* a3,
-                      float* x1s, __half* x1s_split32, int B, int H, int W, cudaStream_t st);
+                      float* x1s, __half* x1s_split32, int B, int H, int W, cudaStream_t st, int tc_tail = 0);
 int launch_fuse_pyramid(const float* x3, const float* x4, const float* x5, float* out, __half* out_split, int B, int H3,
                         int W3, cudaStream_t st);
 int launch_reliability(const xfeat_ctx* ctx, const float* t, float* out, int64_t npix, cudaStream_t st);

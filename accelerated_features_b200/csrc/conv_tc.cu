@@ -34,20 +34,24 @@ constexpr int CT_ABOX = 128 * 128;   // bytes: 128 pixels x 128 B (64 halves)
 template <int KS, int CINP, int NOUT>
 struct ConvTcCfg {
   static constexpr int TAPS = KS * KS;
-  static constexpr int A_BOXES = CINP / 32;                           // 1 or 2
-  static constexpr int A_STAGE = A_BOXES * CT_ABOX;
-  static constexpr int W_GROUP = NOUT * 128;                          // bytes
+  static constexpr int ROWB = (CINP == 8) ? 32 : 128;                 // operand row bytes ([hi(8)|lo(8)] halves for the stem)
+  static constexpr int KSTEPS = ROWB / 32;
+  static constexpr int A_BOXES = (CINP == 64) ? 2 : 1;
+  static constexpr int A_STAGE = A_BOXES * 128 * ROWB;
+  static constexpr int W_GROUP = NOUT * ROWB;                         // bytes
   static constexpr size_t W_BYTES = (size_t)TAPS * 2 * W_GROUP;
   static constexpr int NS_MAX = (int)((227 * 1024 - 2048 - W_BYTES) / A_STAGE);
-  static constexpr int NS = NS_MAX > 6 ? 6 : NS_MAX;                  // A stages (one tap each)
+  static constexpr int NS_CAP = (CINP == 8) ? 20 : 6;                 // 4 KB stages: many in flight to cover TMA latency
+  static constexpr int NS = NS_MAX > NS_CAP ? NS_CAP : NS_MAX;        // A stages (one tap each)
   static constexpr size_t A_BYTES = (size_t)NS * A_STAGE;
-  static constexpr size_t SMEM = 1024 + W_BYTES + A_BYTES + 768;
+  static constexpr size_t SMEM = 1024 + W_BYTES + A_BYTES + 1536;
   // accumulator per buffer: columns [0,NOUT) = terms against weight group 0, [NOUT,2*NOUT) = against group 1: a single UMMA
   // with N = 2*NOUT reads the activation operand once for both groups (the layers are shared-memory-bandwidth bound).
   static constexpr int ACC_COLS = 2 * NOUT;
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;                      // two accumulator buffers
+  static constexpr int NACC = (512 / ACC_COLS) > 8 ? 8 : (512 / ACC_COLS);   // accumulator ring (see conv_tc_halo.cu)
+  static constexpr int TMEM_COLS = NACC * ACC_COLS;
   static_assert(NS >= 2, "need at least two A stages");
-  static_assert(CINP == 32 || CINP == 64, "CINP");
+  static_assert(CINP == 8 || CINP == 32 || CINP == 64, "CINP");
   static_assert(NOUT == 32 || NOUT == 64, "NOUT");
 };
 
@@ -65,6 +69,9 @@ struct ConvTcParams {
   float* out_f32;     // (B,H,W,f32_c) or null; this CTA's channels start at f32_co0, n_real of them are real
   int f32_c, f32_co0, n_real;
   int relu;
+  // optional skip branch of the stem (model.py:40-41,140): out += avgpool4(xn) * skip_w + skip_b, xn = (B, 4H, 4W) fp32
+  const float* skip_xn;
+  const float* skip_w;   // 24 weights then 24 biases
 };
 
 template <int KS, int CINP, int NOUT>
@@ -78,9 +85,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;                 // [NS]
   uint64_t* a_empty = bars + 1 + C::NS;        // [NS]
-  uint64_t* acc_full = bars + 1 + 2 * C::NS;   // [2]
-  uint64_t* acc_empty = acc_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  constexpr int NACC = C::NACC;
+  uint64_t* acc_full = bars + 1 + 2 * C::NS;   // [NACC]
+  uint64_t* acc_empty = acc_full + NACC;       // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
   float* sBias = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,6 +98,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   const int n_tiles = tiles_img * P.B;
 
   if (threadIdx.x < NOUT) sBias[threadIdx.x] = (threadIdx.x < P.n_real) ? __ldg(P.bias + threadIdx.x) : 0.f;
+  float* sSkip = sBias + NOUT;   // [2][NOUT]: skip weights, skip biases (zero when unused / padded)
+  if (threadIdx.x < 2 * NOUT) {
+    const int c = threadIdx.x % NOUT, wb = threadIdx.x / NOUT;
+    sSkip[threadIdx.x] = (P.skip_w != nullptr && c < 24) ? __ldg(P.skip_w + wb * 24 + c) : 0.f;
+  }
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&P.amap);
     tc::tma_prefetch_desc(&P.wmap);
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
       tc::mbar_init(&a_full[i], 1);
       tc::mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NACC; ++i) {
       tc::mbar_init(&acc_full[i], 1);
       tc::mbar_init(&acc_empty[i], 4);
     }
@@ -114,7 +127,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // ---------------- TMA producer ----------------
       tc::mbar_expect_tx(w_full, (uint32_t)C::W_BYTES);
       for (int i = 0; i < C::TAPS * 2; ++i) tc::tma_load_2d(sW + (size_t)i * C::W_GROUP, &P.wmap, w_full, 0, i * NOUT);
@@ -136,15 +149,15 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);
       constexpr uint32_t idesc2 = tc::make_idesc(/*F16*/ 0, 128, 2 * NOUT);
       tc::mbar_wait(w_full, 0);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        const int a = tcount & 1;
-        tc::mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
+        const int a = tcount % NACC;
+        tc::mbar_wait(&acc_empty[a], ((tcount / NACC) & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t d = tmem + a * C::ACC_COLS;
         for (int tap = 0; tap < C::TAPS; ++tap, ++it) {
@@ -153,8 +166,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
           tc::tc_fence_after();
           const uint32_t a_addr = tc::smem_u32(sA + (size_t)s * C::A_STAGE);
           const uint32_t w_addr = tc::smem_u32(sW + (size_t)tap * 2 * C::W_GROUP);
-          const uint64_t a0 = tc::make_desc_sw128(a_addr, 1024);
-          const uint64_t w0 = tc::make_desc_sw128(w_addr, 1024);   // group 0, and (N = 2*NOUT) groups [0 ; 1] stacked
+          const uint64_t a0 = tc::make_desc_rows<C::ROWB>(a_addr);
+          const uint64_t w0 = tc::make_desc_rows<C::ROWB>(w_addr);   // group 0, and (N = 2*NOUT) groups [0 ; 1] stacked
           if (C::A_BOXES == 2) {
             const uint64_t a1 = tc::make_desc_sw128(a_addr + CT_ABOX, 1024);
 #pragma unroll
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int k = 0; k < 4; ++k) tc::umma_f16(d, a1 + 2 * k, w0 + 2 * k, idesc, 1u);                    // lo.whi
           } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc2, (tap | k) ? 1u : 0u);  // [hi|lo].[[whi|whi];[wlo|0]]
+            for (int k = 0; k < C::KSTEPS; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc2, (tap | k) ? 1u : 0u);  // [hi|lo].[[whi|whi];[wlo|0]]
           }
           tc::umma_commit(&a_empty[s]);
         }
@@ -178,10 +191,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     const int ph_ = r >> P.tw_log2, pw_ = r & (TW - 1);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-      const int a = tcount & 1;
+      const int a = tcount % NACC;
       const int b = tile / tiles_img, rem = tile - b * tiles_img;
       const int y = (rem / tiles_x) * TH + ph_, x = (rem % tiles_x) * TW + pw_;
-      tc::mbar_wait(&acc_full[a], (tcount >> 1) & 1);
+      tc::mbar_wait(&acc_full[a], (tcount / NACC) & 1);
       tc::tc_fence_after();
       uint32_t v[2 * NOUT];
       __syncwarp();
@@ -204,6 +217,20 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
           float t0 = fmaf(__uint_as_float(v[c]) + __uint_as_float(v[NOUT + c]), P.inv_wscale, sBias[c]);
           if (P.relu) t0 = fmaxf(t0, 0.f);
           o[c] = t0;
+        }
+        if (P.skip_xn != nullptr) {
+          // AvgPool2d(4,4) of the normalised gray image, then 1x1 conv 1 -> 24 with bias, added AFTER the ReLU (model.py:140)
+          const int W0 = P.W * 4;
+          const float* xp = P.skip_xn + ((int64_t)b * P.H * 4 + y * 4) * W0 + x * 4;
+          float sacc = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(xp + (int64_t)rr * W0));
+            sacc += t.x; sacc += t.y; sacc += t.z; sacc += t.w;
+          }
+          const float skipv = sacc * (1.0f / 16.0f);
+#pragma unroll
+          for (int c = 0; c < NOUT; ++c) o[c] += fmaf(skipv, sSkip[c], sSkip[NOUT + c]);
         }
         if (P.out_f32) {
           float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * P.f32_c + P.f32_co0);
@@ -297,7 +324,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int b = tile / tiles_img, rem = tile - b * tiles_img;
@@ -318,7 +345,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);
       constexpr uint32_t idesc2 = tc::make_idesc(/*F16*/ 0, 128, 2 * NOUT);
       uint32_t it = 0, tcount = 0;
@@ -491,6 +518,8 @@ static bool tc_layer_cfg(int layer, TcLayer& c) {
   const LayerSpec& s = kLayers[layer];
   if (s.cin == 64 && s.cout == 64) { c = {64, 64, 1}; return true; }            // block3.1/2, block4.*, fusion, heads
   if (s.cin == 24 && s.cout == 24) { c = {32, 32, 1}; return true; }            // block2 (channels padded 24 -> 32)
+  if (s.cin == 8 && s.cout == 8) { c = {8, 8, 1}; return true; }                // block1.2 (halo kernel only), 32-byte operand rows
+  if (s.cin == 8 && s.cout == 24) { c = {8, 32, 1}; return true; }              // block1.3 (stride 2) + skip1
   if (s.cin == 24 && s.cout == 64) { c = {32, 64, 1}; return true; }            // block3.0 (stride 2)
   if (s.cin == 64 && s.cout == 128) { c = {64, 64, 2}; return true; }           // block5.0 (stride 2), two N tiles
   if (s.cin == 128 && s.stride == 1) { c = {128, 64, s.cout / 64}; return true; }   // block5.1/5.2 (3x3), block5.3 (1x1): streamed weights
@@ -511,7 +540,7 @@ int conv_tc_prepare(xfeat_ctx* ctx) {
     TcLayer c;
     if (tc_layer_cfg(l, c)) {
       ctx->tc_off[l] = total;
-      total += (size_t)c.ntiles * kLayers[l].ks * kLayers[l].ks * 2 * c.nout * 64 * (c.cinp == 128 ? 2 : 1);
+      total += (size_t)c.ntiles * kLayers[l].ks * kLayers[l].ks * 2 * c.nout * 64 * (c.cinp == 128 ? 2 : 1);   // (8-channel layers use 16 of the 64 halves per row slot: simpler indexing, 36 KB wasted)
     }
   }
   std::vector<__half> h(total, __float2half_rn(0.f));
@@ -544,20 +573,21 @@ int conv_tc_prepare(xfeat_ctx* ctx) {
           }
       continue;
     }
+    const int rowh = (c.cinp == 8) ? 16 : 64;   // halves per weight row
     for (int nt = 0; nt < c.ntiles; ++nt) {
-      __half* dst = h.data() + ctx->tc_off[l] + (size_t)nt * taps * 2 * c.nout * 64;
+      __half* dst = h.data() + ctx->tc_off[l] + (size_t)nt * taps * 2 * c.nout * rowh;
       for (int t = 0; t < taps; ++t)
         for (int n = 0; n < c.nout; ++n) {
           const int co = nt * c.nout + n;
-          __half* g0 = dst + (((size_t)t * 2 + 0) * c.nout + n) * 64;
-          __half* g1 = dst + (((size_t)t * 2 + 1) * c.nout + n) * 64;
+          __half* g0 = dst + (((size_t)t * 2 + 0) * c.nout + n) * rowh;
+          __half* g1 = dst + (((size_t)t * 2 + 1) * c.nout + n) * rowh;
           if (co >= sp.cout) continue;                                 // padded output channel: zero row
           for (int ci = 0; ci < sp.cin; ++ci) {
             const float v = w[((size_t)t * sp.cin + ci) * sp.cout + co] * s;
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn(v - __half2float(hi));
             if (c.cinp == 64) { g0[ci] = hi; g1[ci] = lo; }
-            else { g0[ci] = hi; g0[32 + ci] = hi; g1[ci] = lo; }      // [whi|whi], [wlo|0]
+            else { g0[ci] = hi; g0[c.cinp + ci] = hi; g1[ci] = lo; }  // [whi|whi], [wlo|0]  (cinp = 32 or 8)
           }
         }
     }
@@ -594,10 +624,11 @@ static int launch_tc_cfg(const ConvTcParams& P, int grid, cudaStream_t st) {
 
 // in_split: (B,Hin,Win,2*CINP) halves [hi|lo].  out_split (optional): (B,Ho,Wo,2*NOUT); out_f32 (optional): (B,Ho,Wo,cout).
 int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int Hin, int Win, __half* out_split,
-                   float* out_f32, cudaStream_t st) {
+                   float* out_f32, cudaStream_t st, const float* skip_xn) {
   TcLayer c;
   XF_REQUIRE(tc_layer_cfg(layer, c) && ctx->d_tcw, "conv_tc: layer %d not prepared for the tensor-core path", layer);
   XF_REQUIRE(out_split || out_f32, "conv_tc: no output");
+  XF_REQUIRE(!(c.cinp == 8 && c.nout == 8 && g_conv_impl != 2), "conv_tc: block1.2 runs on the halo kernel only (conv impl 2)");
   if (g_conv_impl == 2 && kLayers[layer].ks == 3 && kLayers[layer].stride == 1 && c.ntiles == 1 && c.cinp == c.nout)
     return launch_conv_tc_halo(ctx, layer, in_split, B, Hin, Win, out_split, out_f32, st);
   PFN_encodeTiled enc = get_encode_tiled();
@@ -611,14 +642,15 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
   int tw_log2;
   pick_tile(Ho, Wo, tw_log2);
   const int TW = 1 << tw_log2, TH = 128 >> tw_log2;
+  const int rowh = (c.cinp == 8) ? 16 : 64;
+  const CUtensorMapSwizzle swz = (c.cinp == 8) ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   const cuuint64_t row_bytes = (cuuint64_t)2 * c.cinp * sizeof(__half);
   const cuuint64_t dims[4] = {(cuuint64_t)2 * c.cinp, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
   const cuuint64_t strides[3] = {row_bytes, (cuuint64_t)Win * row_bytes, (cuuint64_t)Hin * Win * row_bytes};
-  const cuuint32_t box[4] = {64, (cuuint32_t)(TW * S), (cuuint32_t)(TH * S), 1};
+  const cuuint32_t box[4] = {(cuuint32_t)rowh, (cuuint32_t)(TW * S), (cuuint32_t)(TH * S), 1};
   const cuuint32_t estr[4] = {1, (cuuint32_t)S, (cuuint32_t)S, 1};
   CUresult r = enc(&P.amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)in_split, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activations %dx%dx%d, stride %d) failed: %d", B, Hin, Win, S, (int)r);
     return XF_E_CUDA;
@@ -633,6 +665,8 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
   P.out_f32 = out_f32;
   P.f32_c = sp.cout;
   P.relu = sp.relu;
+  P.skip_xn = skip_xn;
+  P.skip_w = skip_xn ? ctx->d_weights + ctx->table.w_off[L_SKIP1] : nullptr;   // 24 weights; the 24 biases follow (layers.h packing)
   const int n_tiles = cdiv(Ho, TH) * cdiv(Wo, TW) * B;
   const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
   P.split_c = sp.cout <= 32 ? 32 : sp.cout;   // channel count of the split output tensor [hi(split_c) | lo(split_c)]
@@ -665,13 +699,13 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
     return XF_OK;
   }
   for (int nt = 0; nt < c.ntiles; ++nt) {
-    const cuuint64_t wdims[2] = {64, (cuuint64_t)taps * 2 * c.nout};
-    const cuuint64_t wstrides[1] = {128};
-    const cuuint32_t wbox[2] = {64, (cuuint32_t)c.nout};
+    const cuuint64_t wdims[2] = {(cuuint64_t)rowh, (cuuint64_t)taps * 2 * c.nout};
+    const cuuint64_t wstrides[1] = {(cuuint64_t)rowh * 2};
+    const cuuint32_t wbox[2] = {(cuuint32_t)rowh, (cuuint32_t)c.nout};
     const cuuint32_t westr[2] = {1, 1};
-    __half* wptr = (__half*)ctx->d_tcw + ctx->tc_off[layer] + (size_t)nt * taps * 2 * c.nout * 64;
+    __half* wptr = (__half*)ctx->d_tcw + ctx->tc_off[layer] + (size_t)nt * taps * 2 * c.nout * rowh;
     r = enc(&P.wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)wptr, wdims, wstrides, wbox, westr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(weights, layer %d) failed: %d", layer, (int)r);
       return XF_E_CUDA;
@@ -684,6 +718,7 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
     else if (sp.ks == 1 && c.cinp == 64 && c.nout == 64) rc = launch_tc_cfg<1, 64, 64>(P, grid, st);
     else if (sp.ks == 3 && c.cinp == 32 && c.nout == 32) rc = launch_tc_cfg<3, 32, 32>(P, grid, st);
     else if (sp.ks == 3 && c.cinp == 32 && c.nout == 64) rc = launch_tc_cfg<3, 32, 64>(P, grid, st);
+    else if (sp.ks == 3 && c.cinp == 8 && c.nout == 32) rc = launch_tc_cfg<3, 8, 32>(P, grid, st);
     else {
       set_error("conv_tc: no kernel instantiation for layer %d", layer);
       return XF_E_UNSUPPORTED;
@@ -700,12 +735,12 @@ extern "C" int xfeat_debug_conv_layer_tc(xfeat_ctx* ctx, int layer, const float*
                                          void* d_scratch, size_t scratch_bytes, void* stream) {
   XF_REQUIRE(ctx && d_in && d_out && d_scratch && layer >= 0 && layer < xf::L_COUNT, "debug_conv_layer_tc: bad arguments");
   XF_REQUIRE(xf::conv_tc_eligible(layer), "debug_conv_layer_tc: layer %d has no tensor-core configuration", layer);
-  const int cin = xf::kLayers[layer].cin, cinp = cin <= 32 ? 32 : (cin <= 64 ? 64 : 128);
+  const int cin = xf::kLayers[layer].cin, cinp = cin <= 8 ? 8 : (cin <= 32 ? 32 : (cin <= 64 ? 64 : 128));
   const int64_t npix = (int64_t)B * H * W;
   XF_REQUIRE(scratch_bytes >= (size_t)npix * 4 * cinp, "debug_conv_layer_tc: scratch must hold B*H*W*%d bytes", 4 * cinp);
   XF_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   int rc = xf::launch_split_nhwc(d_in, (__half*)d_scratch, npix, cin, cinp, st);
   if (rc) return rc;
-  return xf::launch_conv_tc(ctx, layer, (const __half*)d_scratch, B, H, W, nullptr, d_out, st);
+  return xf::launch_conv_tc(ctx, layer, (const __half*)d_scratch, B, H, W, nullptr, d_out, st, nullptr);
 }

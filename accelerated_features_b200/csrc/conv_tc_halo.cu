@@ -23,16 +23,21 @@ constexpr int CH_PATCH64_BYTES = 27648; // CINP=64: PW <= 42 (TW <= 40): 214 row
 
 template <int CINP, int NOUT>
 struct HaloCfg {
-  static constexpr int W_GROUP = NOUT * 128;
+  static constexpr int ROWB = (CINP == 8) ? 32 : 128;     // bytes per operand row: [hi(8)|lo(8)] halves, or 64 halves
+  static constexpr int KSTEPS = ROWB / 32;                // UMMA K = 16 halves = 32 B
+  static constexpr int W_GROUP = NOUT * ROWB;
   static constexpr size_t W_BYTES = (size_t)9 * 2 * W_GROUP;
   // patch buffers: CINP=32 -> 4-deep ring over tiles; CINP=64 -> 3-deep ring over the sequence hi(t), lo(t), hi(t+1), ...
-  static constexpr int NP = (CINP == 32) ? 4 : 3;
-  static constexpr int PB = (CINP == 32) ? CH_PATCH_BYTES : CH_PATCH64_BYTES;
-  static constexpr size_t SMEM = 1024 + W_BYTES + NP * (size_t)PB + 768;
+  static constexpr int NP = (CINP == 64) ? 3 : (CINP == 32 ? 4 : 16);
+  static constexpr int PB = (CINP == 64) ? CH_PATCH64_BYTES : (CINP == 32 ? CH_PATCH_BYTES : CH_PATCH_BYTES / 4);
+  static constexpr size_t SMEM = 1024 + W_BYTES + NP * (size_t)PB + 1024;
   // accumulator per buffer: columns [0,NOUT) = terms against whi, [NOUT,2*NOUT) = terms against wlo (one UMMA with
   // N = 2*NOUT reads the activation operand once for both weight groups); the epilogue adds the two halves.
   static constexpr int ACC_COLS = 2 * NOUT;
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  // accumulator ring: the MMA -> epilogue -> MMA round trip (commit, mbarrier wake-up, tcgen05.ld, arrive) costs ~1-2k cycles,
+  // far more than the MMAs of a thin tile, so several tiles are kept in flight in TMEM (512 columns available).
+  static constexpr int NACC = (512 / ACC_COLS) > 8 ? 8 : (512 / ACC_COLS);
+  static constexpr int TMEM_COLS = NACC * ACC_COLS < 32 ? 32 : NACC * ACC_COLS;
 };
 
 struct HaloParams {
@@ -54,6 +59,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128_at(uint32_t smem_addr, uint3
   if (mode) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
   return d;
 }
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc_rows_at(uint32_t smem_addr, int mode) {
+  return ROWB == 128 ? make_desc_sw128_at(smem_addr, 1024, mode) : tc::make_desc_sw32(smem_addr, 256);
+}
 
 template <int CINP, int NOUT>
 __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ HaloParams P) {
@@ -68,16 +77,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
   uint64_t* w_full = bars;
   uint64_t* p_full = bars + 1;            // [NP]
   uint64_t* p_empty = bars + 1 + NP;      // [NP]
-  uint64_t* acc_full = bars + 1 + 2 * NP; // [2]
-  uint64_t* acc_empty = acc_full + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  constexpr int NACC = C::NACC;
+  uint64_t* acc_full = bars + 1 + 2 * NP; // [NACC]
+  uint64_t* acc_empty = acc_full + NACC;  // [NACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
   float* sBias = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_x = (P.W + P.TW - 1) / P.TW, tiles_y = (P.H + P.TH - 1) / P.TH;
   const int tiles_img = tiles_x * tiles_y;
   const int n_tiles = tiles_img * P.B;
-  const uint32_t patch_tx = (uint32_t)(P.TH + 2) * P.PW * 128;
+  constexpr int ROWB = C::ROWB, KSTEPS = C::KSTEPS;
+  const uint32_t patch_tx = (uint32_t)(P.TH + 2) * P.PW * ROWB;
 
   if (threadIdx.x < NOUT) sBias[threadIdx.x] = (threadIdx.x < P.n_real) ? __ldg(P.bias + threadIdx.x) : 0.f;
   if (warp == 0 && lane == 0) {
@@ -88,7 +99,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
       tc::mbar_init(&p_full[i], 1);
       tc::mbar_init(&p_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NACC; ++i) {
       tc::mbar_init(&acc_full[i], 1);
       tc::mbar_init(&acc_empty[i], 4);
     }
@@ -107,7 +118,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
   //            tile run first so the next tile's hi patch can stream in while the lo MMAs run, and vice versa).
   // CINP = 32: a ring of NP buffers over tiles (rows are [hi(32)|lo(32)]): the producer runs up to NP-1 tiles ahead.
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(w_full, (uint32_t)C::W_BYTES);
       for (int i = 0; i < 18; ++i) tc::tma_load_2d(sW + (size_t)i * C::W_GROUP, &P.wmap, w_full, 0, i * NOUT);
       uint32_t tcount = 0;
@@ -133,15 +144,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, NOUT);        // against one weight group
       constexpr uint32_t idesc2 = tc::make_idesc(/*F16*/ 0, 128, 2 * NOUT);   // against [group0 ; group1] stacked along N
       tc::mbar_wait(w_full, 0);
       const uint32_t w_base = tc::smem_u32(sW);
       uint32_t tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        const int a = tcount & 1;
-        tc::mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
+        const int a = tcount % NACC;
+        tc::mbar_wait(&acc_empty[a], ((tcount / NACC) & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t d = tmem + a * C::ACC_COLS;
         if (CINP == 64) {
@@ -174,11 +185,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
           tc::mbar_wait(&p_full[s], (tcount / NP) & 1);
           tc::tc_fence_after();
           for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * 128u;
-            const uint64_t a0 = make_desc_sw128_at(p_base + shift, 1024, P.desc_mode);
-            const uint64_t wboth = tc::make_desc_sw128(w_base + (uint32_t)(tap * 2) * C::W_GROUP, 1024);
+            const uint32_t shift = (uint32_t)((tap / 3) * P.PW + (tap % 3)) * (uint32_t)ROWB;
+            const uint64_t a0 = make_desc_rows_at<ROWB>(p_base + shift, P.desc_mode);
+            const uint64_t wboth = tc::make_desc_rows<ROWB>(w_base + (uint32_t)(tap * 2) * C::W_GROUP);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)   // [hi|lo] . [[whi|whi] ; [wlo|0]]  ->  cols [0,32): hi.whi + lo.whi, cols [32,64): hi.wlo
+            for (int k = 0; k < KSTEPS; ++k)   // [hi|lo] . [[whi|whi] ; [wlo|0]]  ->  cols [0,N): hi.whi + lo.whi, cols [N,2N): hi.wlo
               tc::umma_f16(d, a0 + 2 * k, wboth + 2 * k, idesc2, (tap | k) ? 1u : 0u);
           }
           tc::umma_commit(&p_empty[s]);
@@ -194,19 +205,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
     const bool lane_ok = (mh < P.TH) && (mw < P.TW);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-      const int a = tcount & 1;
+      const int a = tcount % NACC;
       const int b = tile / tiles_img, rem = tile - b * tiles_img;
       const int y = (rem / tiles_x) * P.TH + mh, x = (rem % tiles_x) * P.TW + mw;
-      tc::mbar_wait(&acc_full[a], (tcount >> 1) & 1);
+      tc::mbar_wait(&acc_full[a], (tcount / NACC) & 1);
       tc::tc_fence_after();
       uint32_t v[2 * NOUT];
       __syncwarp();
+      if constexpr (NOUT == 8) {
+        tc::tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + a * C::ACC_COLS, v);
+      } else {
 #pragma unroll
-      for (int c = 0; c < 2 * NOUT / 32; ++c) {
-        uint32_t t[32];
-        tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * C::ACC_COLS + c * 32, t);
+        for (int c = 0; c < 2 * NOUT / 32; ++c) {
+          uint32_t t[32];
+          tc::tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + a * C::ACC_COLS + c * 32, t);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[c * 32 + j] = t[j];
+          for (int j = 0; j < 32; ++j) v[c * 32 + j] = t[j];
+        }
       }
       tc::tmem_ld_wait();
       tc::tc_fence_before();
@@ -278,9 +293,11 @@ int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split,
   const LayerSpec& sp = kLayers[layer];
   XF_REQUIRE(sp.ks == 3 && sp.stride == 1 && ctx->d_tcw && ctx->tc_off[layer] != (size_t)-1,
              "conv_tc_halo: layer %d is not a prepared 3x3 stride-1 layer", layer);
-  const bool c64 = (sp.cin == 64 && sp.cout == 64), c32 = (sp.cin == 24 && sp.cout == 24);
-  XF_REQUIRE(c64 || c32, "conv_tc_halo: unsupported channel configuration");
-  const int cinp = c64 ? 64 : 32, nout = cinp;
+  const bool c64 = (sp.cin == 64 && sp.cout == 64), c32 = (sp.cin == 24 && sp.cout == 24), c8 = (sp.cin == 8 && sp.cout == 8);
+  XF_REQUIRE(c64 || c32 || c8, "conv_tc_halo: unsupported channel configuration");
+  const int cinp = c64 ? 64 : (c32 ? 32 : 8), nout = cinp;
+  const int rowh = c8 ? 16 : 64;                       // halves per operand row
+  const CUtensorMapSwizzle swz = c8 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -292,22 +309,20 @@ int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split,
   const cuuint64_t row_bytes = (cuuint64_t)2 * cinp * sizeof(__half);
   const cuuint64_t dims[4] = {(cuuint64_t)2 * cinp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t strides[3] = {row_bytes, (cuuint64_t)W * row_bytes, (cuuint64_t)H * W * row_bytes};
-  const cuuint32_t box[4] = {64, (cuuint32_t)P.PW, (cuuint32_t)(P.TH + 2), 1};
+  const cuuint32_t box[4] = {(cuuint32_t)rowh, (cuuint32_t)P.PW, (cuuint32_t)(P.TH + 2), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&P.amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)in_split, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(halo activations) failed: %d", (int)r);
     return XF_E_CUDA;
   }
-  const cuuint64_t wdims[2] = {64, (cuuint64_t)18 * nout};
-  const cuuint64_t wstrides[1] = {128};
-  const cuuint32_t wbox[2] = {64, (cuuint32_t)nout};
+  const cuuint64_t wdims[2] = {(cuuint64_t)rowh, (cuuint64_t)18 * nout};
+  const cuuint64_t wstrides[1] = {(cuuint64_t)rowh * 2};
+  const cuuint32_t wbox[2] = {(cuuint32_t)rowh, (cuuint32_t)nout};
   const cuuint32_t westr[2] = {1, 1};
   r = enc(&P.wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)((__half*)ctx->d_tcw + ctx->tc_off[layer]), wdims, wstrides, wbox,
-          westr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          westr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(halo weights) failed: %d", (int)r);
     return XF_E_CUDA;
@@ -330,13 +345,20 @@ int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split,
       attr = true;
     }
     conv_tc_halo_kernel<64, 64><<<grid, CH_THREADS, HaloCfg<64, 64>::SMEM, st>>>(P);
-  } else {
+  } else if (c32) {
     static bool attr = false;
     if (!attr) {
       XF_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HaloCfg<32, 32>::SMEM));
       attr = true;
     }
     conv_tc_halo_kernel<32, 32><<<grid, CH_THREADS, HaloCfg<32, 32>::SMEM, st>>>(P);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      XF_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HaloCfg<8, 8>::SMEM));
+      attr = true;
+    }
+    conv_tc_halo_kernel<8, 8><<<grid, CH_THREADS, HaloCfg<8, 8>::SMEM, st>>>(P);
   }
   XF_LAUNCH_CHECK();
   return XF_OK;

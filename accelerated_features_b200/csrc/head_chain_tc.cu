@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       tc::mbar_expect_tx(w_full, (uint32_t)W_BYTES);
       for (int l = 0; l < NH; ++l)
         for (int g = 0; g < 2; ++g) tc::tma_load_2d(sW + (size_t)(l * 2 + g) * HC_WBOX, &P.wmap[l], w_full, 0, g * 64);
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       constexpr uint32_t idesc_h = tc::make_idesc(0, 128, 64);
       constexpr uint32_t idesc_f = tc::make_idesc(0, 128, NF);
       tc::mbar_wait(w_full, 0);

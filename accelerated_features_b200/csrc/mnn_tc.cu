@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // ---------------- TMA producer ----------------
       const int arow = pair * n_pad + row0;
       tc::mbar_expect_tx(a_full, 6 * TC_BOX_BYTES);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (tc::elect_one()) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, TC_BN);
       tc::mbar_wait(a_full, 0);

@@ -108,6 +108,24 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const __grid_constant__ 
       return;
     }
   }
+  if constexpr (COUT == 8) {
+    if (out_split32 != nullptr) {
+      // feed the tensor-core block1.2: [hi(8) | lo(8)] fp16 per pixel = 32 bytes (conv_tc_halo.cu, 32-byte operand rows)
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2 h = __floats2half2_rn(res[2 * j], res[2 * j + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(res[2 * j] - hf.x, res[2 * j + 1] - hf.y);
+        hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      uint4* sp = reinterpret_cast<uint4*>(out_split32 + (((int64_t)b * Ho + oy) * Wo + ox) * 16);
+      sp[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      sp[1] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      return;
+    }
+  }
   float* op = out + (((int64_t)b * Ho + oy) * Wo + ox) * COUT;
 #pragma unroll
   for (int c4 = 0; c4 < COUT / 4; ++c4)
@@ -131,14 +149,17 @@ static int launch_stem(const float* hw, const float* hb, const float* sw, const 
 }
 
 // xn (B,H,W) -> a1 (B,H,W,4) -> a2 (B,H/2,W/2,8) -> a3 (same,8) -> x1s (B,H/4,W/4,24) = block1(x) + skip1(x)
+// tc_tail != 0: only block1.0 and block1.1 run here (block1.1 writes split fp16 [hi8|lo8] into a2); block1.2 / block1.3 + skip
+// continue on the tensor cores (api.cu).
 int launch_stem_chain(const float* h_weights, const LayerTable& t, const float* xn, float* a1, float* a2, float* a3,
-                      float* x1s, __half* x1s_split32, int B, int H, int W, cudaStream_t st) {
+                      float* x1s, __half* x1s_split32, int B, int H, int W, cudaStream_t st, int tc_tail) {
   const float* hw = h_weights;
   int rc;
   rc = launch_stem<1, 4, 1, false>(hw + t.w_off[L_B1_0], hw + t.b_off[L_B1_0], nullptr, nullptr, xn, nullptr, a1, nullptr, B, H, W, st);
   if (rc) return rc;
-  rc = launch_stem<4, 8, 2, false>(hw + t.w_off[L_B1_1], hw + t.b_off[L_B1_1], nullptr, nullptr, a1, nullptr, a2, nullptr, B, H, W, st);
-  if (rc) return rc;
+  rc = launch_stem<4, 8, 2, false>(hw + t.w_off[L_B1_1], hw + t.b_off[L_B1_1], nullptr, nullptr, a1, nullptr, a2,
+                                   tc_tail ? (__half*)a2 : nullptr, B, H, W, st);
+  if (rc || tc_tail) return rc;
   rc = launch_stem<8, 8, 1, false>(hw + t.w_off[L_B1_2], hw + t.b_off[L_B1_2], nullptr, nullptr, a2, nullptr, a3, nullptr, B, H / 2, W / 2, st);
   if (rc) return rc;
   rc = launch_stem<8, 24, 2, true>(hw + t.w_off[L_B1_3], hw + t.b_off[L_B1_3], hw + t.w_off[L_SKIP1], hw + t.b_off[L_SKIP1],

@@ -45,6 +45,8 @@ CASES = [  # (layer id, oracle prefix, basic layer?, H_in, W_in, pad, stride)
     # 128 input channels: weights streamed per tap
     (14, "block5.1", True, 15, 20, 1, 1), (15, "block5.2", True, 5, 7, 1, 1), (16, "block5.3", True, 15, 20, 0, 1),
     (14, "block5.1", True, 39, 52, 1, 1),
+    # stem tail: 8 input channels, 32-byte operand rows (SWIZZLE_32B), stride 2 (skip branch is covered by the net tests)
+    (3, "block1.3", True, 240, 320, 1, 2), (3, "block1.3", True, 22, 38, 1, 2),
 ]
 
 
