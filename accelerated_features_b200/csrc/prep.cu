@@ -71,26 +71,36 @@ __global__ void __launch_bounds__(256) gray_resize_kernel(const void* __restrict
 __global__ void __launch_bounds__(256) gray_identity_f32_kernel(const float* __restrict__ img, int C, int64_t sb, int64_t sc,
                                                                 int64_t sh, int div255, int H, int W4,
                                                                 float* __restrict__ gray, double* __restrict__ stats) {
+  // each thread: two groups of 4 pixels (x4 and x4 + 64*gridDim.x-stride within the row tile), 2*C 128-bit loads in flight
   const int b = blockIdx.z;
-  const int x4 = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int xa = blockIdx.x * 128 + (threadIdx.x & 63), xb = xa + 64;
   const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  const bool in = (x4 < W4) && (y < H);
-  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (in) {
-    const float* p = img + (int64_t)b * sb + (int64_t)y * sh + 4 * x4;
+  const bool ina = (xa < W4) && (y < H), inb = (xb < W4) && (y < H);
+  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+  if (ina) {
+    const float* p = img + (int64_t)b * sb + (int64_t)y * sh;
     for (int c = 0; c < C; ++c) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(p + (int64_t)c * sc));
-      if (div255) { v.x = __fdiv_rn(v.x, 255.f); v.y = __fdiv_rn(v.y, 255.f); v.z = __fdiv_rn(v.z, 255.f); v.w = __fdiv_rn(v.w, 255.f); }
-      g.x = __fadd_rn(g.x, v.x); g.y = __fadd_rn(g.y, v.y); g.z = __fadd_rn(g.z, v.z); g.w = __fadd_rn(g.w, v.w);
+      float4 va = __ldg(reinterpret_cast<const float4*>(p + (int64_t)c * sc + 4 * xa));
+      float4 vb = inb ? __ldg(reinterpret_cast<const float4*>(p + (int64_t)c * sc + 4 * xb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (div255) {
+        va.x = __fdiv_rn(va.x, 255.f); va.y = __fdiv_rn(va.y, 255.f); va.z = __fdiv_rn(va.z, 255.f); va.w = __fdiv_rn(va.w, 255.f);
+        vb.x = __fdiv_rn(vb.x, 255.f); vb.y = __fdiv_rn(vb.y, 255.f); vb.z = __fdiv_rn(vb.z, 255.f); vb.w = __fdiv_rn(vb.w, 255.f);
+      }
+      ga.x = __fadd_rn(ga.x, va.x); ga.y = __fadd_rn(ga.y, va.y); ga.z = __fadd_rn(ga.z, va.z); ga.w = __fadd_rn(ga.w, va.w);
+      gb.x = __fadd_rn(gb.x, vb.x); gb.y = __fadd_rn(gb.y, vb.y); gb.z = __fadd_rn(gb.z, vb.z); gb.w = __fadd_rn(gb.w, vb.w);
     }
     if (C != 1) {
       const float fc = (float)C;
-      g.x = __fdiv_rn(g.x, fc); g.y = __fdiv_rn(g.y, fc); g.z = __fdiv_rn(g.z, fc); g.w = __fdiv_rn(g.w, fc);
+      ga.x = __fdiv_rn(ga.x, fc); ga.y = __fdiv_rn(ga.y, fc); ga.z = __fdiv_rn(ga.z, fc); ga.w = __fdiv_rn(ga.w, fc);
+      gb.x = __fdiv_rn(gb.x, fc); gb.y = __fdiv_rn(gb.y, fc); gb.z = __fdiv_rn(gb.z, fc); gb.w = __fdiv_rn(gb.w, fc);
     }
-    reinterpret_cast<float4*>(gray + ((int64_t)b * H + y) * (W4 * 4))[x4] = g;
+    float4* row = reinterpret_cast<float4*>(gray + ((int64_t)b * H + y) * (W4 * 4));
+    row[xa] = ga;
+    if (inb) row[xb] = gb;
   }
-  double s = (double)g.x + (double)g.y + (double)g.z + (double)g.w;
-  double ss = (double)g.x * g.x + (double)g.y * g.y + (double)g.z * g.z + (double)g.w * g.w;
+  double s = ((double)ga.x + (double)ga.y) + ((double)ga.z + (double)ga.w) + ((double)gb.x + (double)gb.y) + ((double)gb.z + (double)gb.w);
+  double ss = (double)ga.x * ga.x + (double)ga.y * ga.y + (double)ga.z * ga.z + (double)ga.w * ga.w +
+              (double)gb.x * gb.x + (double)gb.y * gb.y + (double)gb.z * gb.z + (double)gb.w * gb.w;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -244,7 +254,7 @@ extern "C" int xfeat_preprocess(const void* d_img, int dtype, int B, int C, int 
     xf::gray_identity_u8hwc_kernel<<<g4, 256, 0, st>>>((const unsigned char*)d_img, stride_b, stride_h, div255, H, W / 4, d_xn,
                                                        d_stats);
   } else if (fast) {
-    dim3 g4(xf::cdiv(W / 4, 64), xf::cdiv(H, 4), B);
+    dim3 g4(xf::cdiv(W / 4, 128), xf::cdiv(H, 4), B);
     xf::gray_identity_f32_kernel<<<g4, 256, 0, st>>>((const float*)d_img, C, stride_b, stride_c, stride_h, div255, H, W / 4,
                                                      d_xn, d_stats);
   } else if (dtype == XF_DTYPE_F32)

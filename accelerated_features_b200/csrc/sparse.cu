@@ -417,8 +417,10 @@ extern "C" int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const f
   const int64_t npix = (int64_t)B * Hm * Wm;
   xf::feat_norm_kernel<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, st>>>(d_feats, ws.den, npix);
   XF_LAUNCH_CHECK();
-  static const bool use_sorted = getenv("XFEAT_SAMPLE_SORTED") != nullptr;   // experiment knob (default: generic kernel)
-  if (use_sorted && top_k <= xf::SAMPLE_MAX_K && Hm <= xf::SAMPLE_MAX_ROWS) {
+  // one-CTA-per-image spatially ordered variant: L1-friendly, measured 268 vs 330 us at B = 128 x 4096 keypoints; it
+  // needs enough images to fill the GPU (XFEAT_SAMPLE_GENERIC=1 forces the generic kernel)
+  static const bool force_generic = getenv("XFEAT_SAMPLE_GENERIC") != nullptr;
+  if (!force_generic && B >= 32 && top_k <= xf::SAMPLE_MAX_K && Hm <= xf::SAMPLE_MAX_ROWS) {
     const size_t smem = (size_t)top_k * (sizeof(unsigned long long) + sizeof(unsigned short));
     static size_t smem_set = 0;
     if (smem > smem_set) {
