@@ -289,6 +289,12 @@ def run_gpu(args):
         tc = lib.xfeat_get_mnn_impl() == 1
         kname = ("mnn_tc_kernel (tcgen05 split-fp16 K=192 D1.D2^T, fp32 accumulate in TMEM, fused row arg-max, both directions; "
                  "timed call also contains absmax/split/finalize)") if tc else "mnn_scan_kernel (fp32 FFMA D1.D2^T + fused row/col arg-max)"
+        ncu = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01", "ncu_mnn_tc_final.json")) as f:
+                ncu = json.load(f)
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -305,7 +311,12 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"kernel": kname, "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_kind": f"{pk_kind} bf16 dense, sustained", "ms_per_launch": mnn_ms, "traffic": None},
+                         "peak_kind": f"{pk_kind} bf16 dense, sustained", "ms_per_launch": mnn_ms,
+                         "note": "achieved counts each MAC once (SURVEY 8d); the kernel executes 3 fp16 split passes per MAC for fp32-equivalent "
+                                 "results, so tensor-pipe work is 3x this figure",
+                         "tensor_work_frac": 3.0 * achieved / peak if tc else None,
+                         "traffic": (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if (ncu and tc) else None,
+                         "ncu": ncu if tc else None},
         }
         if world == 1 and not args.no_cpu:
             v, total_s, threads = cpu_pairs_per_s(8, 3, 1)

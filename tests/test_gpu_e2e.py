@@ -135,3 +135,40 @@ def test_full_size_properties(xf):
     for b in range(8):
         m = int(cnt[b]); a = idx0[b, :m].cpu().numpy(); bb = idx1[b, :m].cpu().numpy()
         assert len(set(a)) == m and len(set(bb)) == m and np.all(np.diff(a) > 0)
+
+
+def test_batch32_small_images_vs_oracle(xf, oracle_state):
+    """B = 32 routes description through the one-CTA-per-image (spatially ordered) sampler: check it against the oracle."""
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(32, 3, 96, 128, generator=g)
+    want = orc.detect_and_compute(oracle_state, x, 300)
+    got = xf.detectAndCompute(x, top_k=300)
+    worst = 0.0
+    for b in range(32):
+        gk, wk = got[b]["keypoints"].cpu().numpy(), want[b]["keypoints"].numpy()
+        gi = {(float(a), float(c)): i for i, (a, c) in enumerate(gk)}
+        wi = {(float(a), float(c)): i for i, (a, c) in enumerate(wk)}
+        common = set(gi) & set(wi)
+        assert len(common) >= 0.98 * len(wk), (b, len(common), len(wk))
+        ia = np.array([gi[c] for c in common]); ib = np.array([wi[c] for c in common])
+        worst = max(worst, float(np.abs(got[b]["descriptors"].cpu().numpy()[ia] - want[b]["descriptors"].numpy()[ib]).max()))
+    print(f"B=32 sampler: worst descriptor error {worst:.2e}")
+    assert worst < 1e-3
+
+
+def test_star_hd_pair_vs_oracle(xf, oracle_state, assets_vga):
+    """BASELINE config 3 geometry (1280x960, dual scale 768x576 + 1664x1248) on structured images, B = 2, against the oracle."""
+    ref, tgt = assets_vga
+    x1 = torch.nn.functional.interpolate(orc.parse_input(ref), size=(960, 1280), mode="bilinear", align_corners=False)
+    x2 = torch.nn.functional.interpolate(orc.parse_input(tgt), size=(960, 1280), mode="bilinear", align_corners=False)
+    s1, s2 = torch.cat([x1, x2], 0), torch.cat([x2, x1], 0)
+    with torch.inference_mode():
+        want = orc.match_xfeat_star(oracle_state, s1, s2, 4096)
+    got = xf.match_xfeat_star(s1, s2, top_k=4096)
+    assert len(got) == 2
+    for b in range(2):
+        w, g = want[b].numpy(), got[b].cpu().numpy()
+        wd = {(float(r[2]), float(r[3])): r[:2] for r in w}
+        hit = sum(1 for r in g if (float(r[2]), float(r[3])) in wd and np.abs(wd[(float(r[2]), float(r[3]))] - r[:2]).max() < 0.05)
+        print(f"HD star pair {b}: {len(g)} vs {len(w)} refined matches, agreeing {hit}")
+        assert hit >= 0.95 * len(w) and abs(len(g) - len(w)) <= 0.05 * len(w) + 2
