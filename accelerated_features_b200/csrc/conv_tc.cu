@@ -24,7 +24,8 @@
 
 namespace xf {
 
-constexpr int CT_THREADS = 192;
+constexpr int CT_THREADS = 192;    // conv_tc128_kernel: warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int CT_THREADS2 = 320;   // conv_tc_kernel: two epilogue groups (warps 2-5 / 6-9) alternate tiles
 constexpr int CT_ABOX = 128 * 128;   // bytes: 128 pixels x 128 B (64 halves)
 
 // CINP = padded input channels per term (64: two boxes per tap, hi and lo; 32: ONE box per tap whose 128-byte rows are
@@ -37,11 +38,15 @@ struct ConvTcCfg {
   static constexpr int ROWB = (CINP == 8) ? 32 : 128;                 // operand row bytes ([hi(8)|lo(8)] halves for the stem)
   static constexpr int KSTEPS = ROWB / 32;
   static constexpr int A_BOXES = (CINP == 64) ? 2 : 1;
-  static constexpr int A_STAGE = A_BOXES * 128 * ROWB;
+  // CINP = 8: a tap is only 4 KB and one UMMA, so a pipeline stage carries ALL taps of a tile (one barrier round trip per
+  // tile instead of per tap); otherwise one tap per stage.
+  static constexpr int TPS = (CINP == 8) ? TAPS : 1;
+  static constexpr int A_TAP = A_BOXES * 128 * ROWB;
+  static constexpr int A_STAGE = TPS * A_TAP;
   static constexpr int W_GROUP = NOUT * ROWB;                         // bytes
   static constexpr size_t W_BYTES = (size_t)TAPS * 2 * W_GROUP;
   static constexpr int NS_MAX = (int)((227 * 1024 - 2048 - W_BYTES) / A_STAGE);
-  static constexpr int NS_CAP = (CINP == 8) ? 20 : 6;                 // 4 KB stages: many in flight to cover TMA latency
+  static constexpr int NS_CAP = (CINP == 8) ? 4 : 6;
   static constexpr int NS = NS_MAX > NS_CAP ? NS_CAP : NS_MAX;        // A stages (one tap each)
   static constexpr size_t A_BYTES = (size_t)NS * A_STAGE;
   static constexpr size_t SMEM = 1024 + W_BYTES + A_BYTES + 1536;
@@ -75,7 +80,7 @@ struct ConvTcParams {
 };
 
 template <int KS, int CINP, int NOUT>
-__global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
+__global__ void __launch_bounds__(CT_THREADS2, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams P) {
   using C = ConvTcCfg<KS, CINP, NOUT>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -135,15 +140,19 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int b = tile / tiles_img, rem = tile - b * tiles_img;
         const int y0 = (rem / tiles_x) * TH * P.stride - P.pad, x0 = (rem % tiles_x) * TW * P.stride - P.pad;
-        for (int tap = 0; tap < C::TAPS; ++tap, ++it) {
+        for (int tap0 = 0; tap0 < C::TAPS; tap0 += C::TPS, ++it) {
           const int s = it % C::NS;
           const uint32_t ph = (it / C::NS) & 1;
-          const int dy = (KS == 3) ? tap / 3 : 0, dx = (KS == 3) ? tap % 3 : 0;
           tc::mbar_wait(&a_empty[s], ph ^ 1);
           tc::mbar_expect_tx(&a_full[s], C::A_STAGE);
-          unsigned char* dst = sA + (size_t)s * C::A_STAGE;
-          tc::tma_load_4d(dst, &P.amap, &a_full[s], 0, x0 + dx, y0 + dy, b);                    // hi (CINP=64) or [hi|lo]
-          if (C::A_BOXES == 2) tc::tma_load_4d(dst + CT_ABOX, &P.amap, &a_full[s], 64, x0 + dx, y0 + dy, b);  // lo
+#pragma unroll
+          for (int j = 0; j < C::TPS; ++j) {
+            const int tap = tap0 + j;
+            const int dy = (KS == 3) ? tap / 3 : 0, dx = (KS == 3) ? tap % 3 : 0;
+            unsigned char* dst = sA + (size_t)s * C::A_STAGE + (size_t)j * C::A_TAP;
+            tc::tma_load_4d(dst, &P.amap, &a_full[s], 0, x0 + dx, y0 + dy, b);                    // hi (CINP=64) or [hi|lo]
+            if (C::A_BOXES == 2) tc::tma_load_4d(dst + CT_ABOX, &P.amap, &a_full[s], 64, x0 + dx, y0 + dy, b);  // lo
+          }
         }
       }
     }
@@ -160,23 +169,27 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
         tc::mbar_wait(&acc_empty[a], ((tcount / NACC) & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t d = tmem + a * C::ACC_COLS;
-        for (int tap = 0; tap < C::TAPS; ++tap, ++it) {
+        for (int tap0 = 0; tap0 < C::TAPS; tap0 += C::TPS, ++it) {
           const int s = it % C::NS;
           tc::mbar_wait(&a_full[s], (it / C::NS) & 1);
           tc::tc_fence_after();
-          const uint32_t a_addr = tc::smem_u32(sA + (size_t)s * C::A_STAGE);
-          const uint32_t w_addr = tc::smem_u32(sW + (size_t)tap * 2 * C::W_GROUP);
-          const uint64_t a0 = tc::make_desc_rows<C::ROWB>(a_addr);
-          const uint64_t w0 = tc::make_desc_rows<C::ROWB>(w_addr);   // group 0, and (N = 2*NOUT) groups [0 ; 1] stacked
-          if (C::A_BOXES == 2) {
-            const uint64_t a1 = tc::make_desc_sw128(a_addr + CT_ABOX, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc2, (tap | k) ? 1u : 0u);  // hi.whi | hi.wlo
+          for (int j = 0; j < C::TPS; ++j) {
+            const int tap = tap0 + j;
+            const uint32_t a_addr = tc::smem_u32(sA + (size_t)s * C::A_STAGE + (size_t)j * C::A_TAP);
+            const uint32_t w_addr = tc::smem_u32(sW + (size_t)tap * 2 * C::W_GROUP);
+            const uint64_t a0 = tc::make_desc_rows<C::ROWB>(a_addr);
+            const uint64_t w0 = tc::make_desc_rows<C::ROWB>(w_addr);   // group 0, and (N = 2*NOUT) groups [0 ; 1] stacked
+            if (C::A_BOXES == 2) {
+              const uint64_t a1 = tc::make_desc_sw128(a_addr + CT_ABOX, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc::umma_f16(d, a1 + 2 * k, w0 + 2 * k, idesc, 1u);                    // lo.whi
-          } else {
+              for (int k = 0; k < 4; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc2, (tap | k) ? 1u : 0u);  // hi.whi | hi.wlo
 #pragma unroll
-            for (int k = 0; k < C::KSTEPS; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc2, (tap | k) ? 1u : 0u);  // [hi|lo].[[whi|whi];[wlo|0]]
+              for (int k = 0; k < 4; ++k) tc::umma_f16(d, a1 + 2 * k, w0 + 2 * k, idesc, 1u);                    // lo.whi
+            } else {
+#pragma unroll
+              for (int k = 0; k < C::KSTEPS; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc2, (tap | k) ? 1u : 0u);  // [hi|lo].[[whi|whi];[wlo|0]]
+            }
           }
           tc::umma_commit(&a_empty[s]);
         }
@@ -186,11 +199,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc_kernel(const __grid_con
     __syncwarp();
   } else {
     // ---------------- epilogue ----------------
-    const int q = warp & 3;
+    // two epilogue groups (warps 2-5, 6-9) take alternate tiles: the epilogue of a thin tile (TMEM load latency, global
+    // stores, skip-branch loads) is longer than its handful of UMMAs, so two tiles are drained concurrently
+    const int q = warp & 3, eg = (warp - 2) >> 2;
     const int r = q * 32 + lane;                 // pixel of the tile = TMEM lane
     const int ph_ = r >> P.tw_log2, pw_ = r & (TW - 1);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      if ((int)(tcount & 1) != eg) continue;
       const int a = tcount % NACC;
       const int b = tile / tiles_img, rem = tile - b * tiles_img;
       const int y = (rem / tiles_x) * TH + ph_, x = (rem % tiles_x) * TW + pw_;
@@ -617,7 +633,7 @@ static int launch_tc_cfg(const ConvTcParams& P, int grid, cudaStream_t st) {
     XF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, CINP, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     attr = true;
   }
-  conv_tc_kernel<KS, CINP, NOUT><<<grid, CT_THREADS, C::SMEM, st>>>(P);
+  conv_tc_kernel<KS, CINP, NOUT><<<grid, CT_THREADS2, C::SMEM, st>>>(P);
   XF_LAUNCH_CHECK();
   return XF_OK;
 }

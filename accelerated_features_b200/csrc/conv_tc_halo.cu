@@ -17,7 +17,7 @@
 
 namespace xf {
 
-constexpr int CH_THREADS = 192;
+constexpr int CH_THREADS = 320;   // warp 0 TMA, warp 1 MMA, epilogue groups warps 2-5 / 6-9 on alternate tiles
 constexpr int CH_PATCH_BYTES = 34816;   // CINP=32: >= (2*PW + 2 + 128) * 128 for PW <= 66, multiple of 1024
 constexpr int CH_PATCH64_BYTES = 27648; // CINP=64: PW <= 42 (TW <= 40): 214 rows x 128 B, so that THREE buffers fit beside the weights
 
@@ -199,12 +199,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
     }
     __syncwarp();
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3, eg = (warp - 2) >> 2;   // two epilogue groups on alternate tiles (see conv_tc.cu)
     const int m = q * 32 + lane;
     const int mh = m / P.PW, mw = m - mh * P.PW;
     const bool lane_ok = (mh < P.TH) && (mw < P.TW);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      if ((int)(tcount & 1) != eg) continue;
       const int a = tcount % NACC;
       const int b = tile / tiles_img, rem = tile - b * tiles_img;
       const int y = (rem / tiles_x) * P.TH + mh, x = (rem % tiles_x) * P.TW + mw;

@@ -172,3 +172,24 @@ def test_star_hd_pair_vs_oracle(xf, oracle_state, assets_vga):
         hit = sum(1 for r in g if (float(r[2]), float(r[3])) in wd and np.abs(wd[(float(r[2]), float(r[3]))] - r[:2]).max() < 0.05)
         print(f"HD star pair {b}: {len(g)} vs {len(w)} refined matches, agreeing {hit}")
         assert hit >= 0.95 * len(w) and abs(len(g) - len(w)) <= 0.05 * len(w) + 2
+
+
+@pytest.mark.parametrize("hw", [(32, 32), (64, 96), (600, 800), (200, 328)])
+def test_odd_sizes_vs_oracle(xf, oracle_state, assets_vga, hw):
+    """Geometry corner cases of the tensor-core tiles: 1x1 maps at 1/32, partial tiles, non-/32 inputs (resize path)."""
+    ref, tgt = assets_vga
+    H, W = hw
+    x = torch.nn.functional.interpolate(torch.cat([orc.parse_input(ref), orc.parse_input(tgt)], 0), size=(H, W), mode="bilinear",
+                                        align_corners=False)
+    want = orc.detect_and_compute(oracle_state, x, 512)
+    got = xf.detectAndCompute(x, top_k=512)
+    for b in range(2):
+        gk, wk = got[b]["keypoints"].cpu().numpy(), want[b]["keypoints"].numpy()
+        gi = {(float(a), float(c)): i for i, (a, c) in enumerate(gk)}
+        wi = {(float(a), float(c)): i for i, (a, c) in enumerate(wk)}
+        common = set(gi) & set(wi)
+        print(f"{H}x{W} image {b}: {len(gk)} vs {len(wk)} keypoints, common {len(common)}")
+        assert len(common) >= 0.97 * len(wk) - 1
+        if common:
+            ia = np.array([gi[c] for c in common]); ib = np.array([wi[c] for c in common])
+            assert np.abs(got[b]["descriptors"].cpu().numpy()[ia] - want[b]["descriptors"].numpy()[ib]).max() < 1e-3
