@@ -87,6 +87,10 @@ class ClockSampler:
 def cpu_pairs_per_s(n_pairs: int, repeats: int, warmup: int, seed: int = 0):
     import torch
     from oracle import xfeat_oracle as orc
+    # all the host threads torch would use by default (physical cores); torchrun exports OMP_NUM_THREADS=1, undo that here
+    want = max(1, (os.cpu_count() or 2) // 2)
+    if torch.get_num_threads() < want:
+        torch.set_num_threads(want)
     sd = orc.load_state()
     g = torch.Generator().manual_seed(seed)
     x1 = torch.randn(n_pairs, 3, H, W, generator=g)
