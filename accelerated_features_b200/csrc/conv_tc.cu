@@ -77,6 +77,7 @@ struct ConvTcParams {
   // optional skip branch of the stem (model.py:40-41,140): out += avgpool4(xn) * skip_w + skip_b, xn = (B, 4H, 4W) fp32
   const float* skip_xn;
   const float* skip_w;   // 24 weights then 24 biases
+  FastDiv div_img, div_x; // tiles per image, tiles per row
 };
 
 template <int KS, int CINP, int NOUT>
@@ -138,8 +139,9 @@ __global__ void __launch_bounds__(CT_THREADS2, 1) conv_tc_kernel(const __grid_co
       for (int i = 0; i < C::TAPS * 2; ++i) tc::tma_load_2d(sW + (size_t)i * C::W_GROUP, &P.wmap, w_full, 0, i * NOUT);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_img, rem = tile - b * tiles_img;
-        const int y0 = (rem / tiles_x) * TH * P.stride - P.pad, x0 = (rem % tiles_x) * TW * P.stride - P.pad;
+        const int b = (int)fdiv((unsigned)tile, P.div_img), rem = tile - b * tiles_img;
+        const int ty_ = (int)fdiv((unsigned)rem, P.div_x), tx_ = rem - ty_ * tiles_x;
+        const int y0 = ty_ * TH * P.stride - P.pad, x0 = tx_ * TW * P.stride - P.pad;
         for (int tap0 = 0; tap0 < C::TAPS; tap0 += C::TPS, ++it) {
           const int s = it % C::NS;
           const uint32_t ph = (it / C::NS) & 1;
@@ -208,8 +210,9 @@ __global__ void __launch_bounds__(CT_THREADS2, 1) conv_tc_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       if ((int)(tcount & 1) != eg) continue;
       const int a = tcount % NACC;
-      const int b = tile / tiles_img, rem = tile - b * tiles_img;
-      const int y = (rem / tiles_x) * TH + ph_, x = (rem % tiles_x) * TW + pw_;
+      const int b = (int)fdiv((unsigned)tile, P.div_img), rem = tile - b * tiles_img;
+      const int ty_ = (int)fdiv((unsigned)rem, P.div_x), tx_ = rem - ty_ * tiles_x;
+      const int y = ty_ * TH + ph_, x = tx_ * TW + pw_;
       tc::mbar_wait(&acc_full[a], (tcount / NACC) & 1);
       tc::tc_fence_after();
       uint32_t v[2 * NOUT];
@@ -343,8 +346,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
     if (tc::elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_img, rem = tile - b * tiles_img;
-        const int y0 = (rem / tiles_x) * TH - P.pad, x0 = (rem % tiles_x) * TW - P.pad;
+        const int b = (int)fdiv((unsigned)tile, P.div_img), rem = tile - b * tiles_img;
+        const int ty_ = (int)fdiv((unsigned)rem, P.div_x), tx_ = rem - ty_ * tiles_x;
+        const int y0 = ty_ * TH - P.pad, x0 = tx_ * TW - P.pad;
         for (int tap = 0; tap < TAPS; ++tap, ++it) {
           const int s = it % NS;
           const int dy = (KS == 3) ? tap / 3 : 0, dx = (KS == 3) ? tap % 3 : 0;
@@ -397,8 +401,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       const int a = tcount & 1;
-      const int b = tile / tiles_img, rem = tile - b * tiles_img;
-      const int y = (rem / tiles_x) * TH + ph_, x = (rem % tiles_x) * TW + pw_;
+      const int b = (int)fdiv((unsigned)tile, P.div_img), rem = tile - b * tiles_img;
+      const int ty_ = (int)fdiv((unsigned)rem, P.div_x), tx_ = rem - ty_ * tiles_x;
+      const int y = ty_ * TH + ph_, x = tx_ * TW + pw_;
       tc::mbar_wait(&acc_full[a], (tcount >> 1) & 1);
       tc::tc_fence_after();
       uint32_t v0[32], v1[32], v2[32], v3[32];
@@ -684,6 +689,9 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
   P.skip_xn = skip_xn;
   P.skip_w = skip_xn ? ctx->d_weights + ctx->table.w_off[L_SKIP1] : nullptr;   // 24 weights; the 24 biases follow (layers.h packing)
   const int n_tiles = cdiv(Ho, TH) * cdiv(Wo, TW) * B;
+  XF_REQUIRE(n_tiles < (1 << 22), "conv_tc: too many tiles (%d)", n_tiles);
+  P.div_img = make_fastdiv((unsigned)(cdiv(Ho, TH) * cdiv(Wo, TW)));
+  P.div_x = make_fastdiv((unsigned)cdiv(Wo, TW));
   const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
   P.split_c = sp.cout <= 32 ? 32 : sp.cout;   // channel count of the split output tensor [hi(split_c) | lo(split_c)]
   if (c.cinp == 128) {

@@ -51,6 +51,7 @@ struct HaloParams {
   float* out_f32;
   int f32_c, n_real;
   int relu;
+  FastDiv div_img, div_x;
   int desc_mode;      // 0 (default, correct on B200): base_offset = 0; 1: base_offset = (addr >> 7) & 7 (bring-up experiment)
 };
 
@@ -123,8 +124,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
       for (int i = 0; i < 18; ++i) tc::tma_load_2d(sW + (size_t)i * C::W_GROUP, &P.wmap, w_full, 0, i * NOUT);
       uint32_t tcount = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        const int b = tile / tiles_img, rem = tile - b * tiles_img;
-        const int y0 = (rem / tiles_x) * P.TH - 1, x0 = (rem % tiles_x) * P.TW - 1;
+        const int b = (int)fdiv((unsigned)tile, P.div_img), rem = tile - b * tiles_img;
+        const int ty_ = (int)fdiv((unsigned)rem, P.div_x), tx_ = rem - ty_ * tiles_x;
+        const int y0 = ty_ * P.TH - 1, x0 = tx_ * P.TW - 1;
         if (CINP == 64) {
 #pragma unroll
           for (int term = 0; term < 2; ++term) {       // load index li = 2*tcount + term: hi then lo patch of this tile
@@ -207,8 +209,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
       if ((int)(tcount & 1) != eg) continue;
       const int a = tcount % NACC;
-      const int b = tile / tiles_img, rem = tile - b * tiles_img;
-      const int y = (rem / tiles_x) * P.TH + mh, x = (rem % tiles_x) * P.TW + mw;
+      const int b = (int)fdiv((unsigned)tile, P.div_img), rem = tile - b * tiles_img;
+      const int ty_ = (int)fdiv((unsigned)rem, P.div_x), tx_ = rem - ty_ * tiles_x;
+      const int y = ty_ * P.TH + mh, x = tx_ * P.TW + mw;
       tc::mbar_wait(&acc_full[a], (tcount / NACC) & 1);
       tc::tc_fence_after();
       uint32_t v[2 * NOUT];
@@ -338,6 +341,9 @@ int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split,
   P.relu = sp.relu;
   P.desc_mode = g_halo_desc_mode;
   const int n_tiles = cdiv(H, P.TH) * cdiv(W, P.TW) * B;
+  XF_REQUIRE(n_tiles < (1 << 22), "conv_tc_halo: too many tiles (%d)", n_tiles);
+  P.div_img = make_fastdiv((unsigned)(cdiv(H, P.TH) * cdiv(W, P.TW)));
+  P.div_x = make_fastdiv((unsigned)cdiv(W, P.TW));
   const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
   if (c64) {
     static bool attr = false;
