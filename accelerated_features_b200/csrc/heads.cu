@@ -145,6 +145,76 @@ __global__ void __launch_bounds__(KPT_WARPS * 32) kpt_softmax_kernel(const float
   }
 }
 
+// Same fusion, but x3 / x4 / x5 arrive as split fp16 [hi(64) | lo(64)] (x = hi + lo) straight from the tensor-core layers, so
+// block3.2 / block4.2 / block5.3 need not write a second, fp32 copy of their output.
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld_split8(const __half* __restrict__ base, int64_t pix, int c8) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(base + pix * 128 + c8 * 8));
+  const uint4 l = __ldg(reinterpret_cast<const uint4*>(base + pix * 128 + 64 + c8 * 8));
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+  F8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[i])), c = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+    r.v[2 * i] = a.x + c.x;
+    r.v[2 * i + 1] = a.y + c.y;
+  }
+  return r;
+}
+// 8 channels per thread: 128-bit loads of the hi and lo halves (the 64-bit-load version ran at 163 us vs 116 us for fp32 inputs)
+__global__ void __launch_bounds__(256) fuse_pyramid_split_kernel(const __half* __restrict__ x3, const __half* __restrict__ x4,
+                                                                 const __half* __restrict__ x5, __half* __restrict__ out_split,
+                                                                 int H3, int W3, int H4, int W4, int H5, int W5, int64_t total8) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = (int)(i & 7);
+  int64_t p = i >> 3;
+  const int x = (int)(p % W3);
+  p /= W3;
+  const int y = (int)(p % H3);
+  const int b = (int)(p / H3);
+  F8 r = ld_split8(x3, i >> 3, c8);
+  {
+    const LinTap ty = lin_tap(y, (float)H4 / (float)H3, H4), tx = lin_tap(x, (float)W4 / (float)W3, W4);
+    const int64_t bb = (int64_t)b * H4 * W4;
+    const F8 v00 = ld_split8(x4, bb + (int64_t)ty.i0 * W4 + tx.i0, c8), v01 = ld_split8(x4, bb + (int64_t)ty.i0 * W4 + tx.i1, c8);
+    const F8 v10 = ld_split8(x4, bb + (int64_t)ty.i1 * W4 + tx.i0, c8), v11 = ld_split8(x4, bb + (int64_t)ty.i1 * W4 + tx.i1, c8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] += ty.l0 * (tx.l0 * v00.v[k] + tx.l1 * v01.v[k]) + ty.l1 * (tx.l0 * v10.v[k] + tx.l1 * v11.v[k]);
+  }
+  {
+    const LinTap ty = lin_tap(y, (float)H5 / (float)H3, H5), tx = lin_tap(x, (float)W5 / (float)W3, W5);
+    const int64_t bb = (int64_t)b * H5 * W5;
+    const F8 v00 = ld_split8(x5, bb + (int64_t)ty.i0 * W5 + tx.i0, c8), v01 = ld_split8(x5, bb + (int64_t)ty.i0 * W5 + tx.i1, c8);
+    const F8 v10 = ld_split8(x5, bb + (int64_t)ty.i1 * W5 + tx.i0, c8), v11 = ld_split8(x5, bb + (int64_t)ty.i1 * W5 + tx.i1, c8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] += ty.l0 * (tx.l0 * v00.v[k] + tx.l1 * v01.v[k]) + ty.l1 * (tx.l0 * v10.v[k] + tx.l1 * v11.v[k]);
+  }
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __half2 h = __floats2half2_rn(r.v[2 * k], r.v[2 * k + 1]);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(r.v[2 * k] - f.x, r.v[2 * k + 1] - f.y);
+    hw[k] = *reinterpret_cast<const uint32_t*>(&h);
+    lw[k] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  __half* sp = out_split + (i >> 3) * 128 + c8 * 8;
+  *reinterpret_cast<uint4*>(sp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  *reinterpret_cast<uint4*>(sp + 64) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+int launch_fuse_pyramid_split(const __half* x3, const __half* x4, const __half* x5, __half* out_split, int B, int H3, int W3,
+                              cudaStream_t st) {
+  const int64_t total8 = (int64_t)B * H3 * W3 * 8;
+  fuse_pyramid_split_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(x3, x4, x5, out_split, H3, W3, H3 / 2, W3 / 2, H3 / 4,
+                                                                               W3 / 4, total8);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
 int launch_fuse_pyramid(const float* x3, const float* x4, const float* x5, float* out, __half* out_split, int B, int H3,
                         int W3, cudaStream_t st) {
   const int64_t total4 = (int64_t)B * H3 * W3 * 16;

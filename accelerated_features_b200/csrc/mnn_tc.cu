@@ -35,6 +35,8 @@ PFN_encodeTiled get_encode_tiled() {
 constexpr int TC_ROWS = 256, TC_BN = 128, TC_KP = 192, TC_BOX_BYTES = 128 * 128;  // 128 rows x 128 B
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr size_t TC_SMEM = 1024 + 12 * (size_t)TC_BOX_BYTES + 256 + 2 * 128 * 8;
+constexpr int TC1_EPI_WARPS = 16, TC1_THREADS = 64 + 32 * TC1_EPI_WARPS;   // single-pass variant: warps 2-17 epilogue
+constexpr size_t TC1_SMEM = 1024 + 12 * (size_t)TC_BOX_BYTES + 256 + 3 * 2 * 128 * 8 + 2 * 2 * 4 * 128 * 4 + TC1_EPI_WARPS * 64 * 4;
 
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ f, const int* __restrict__ np, int n_max,
                                                      int64_t stride, unsigned* __restrict__ out) {
@@ -265,6 +267,271 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-pass variant (default): S is computed ONCE; the same accumulator tile yields the running row arg-max (as above) and
+// the column arg-max.  A thread owns a row, so a column maximum is a reduction across the 32 lanes of a warp:
+//   1. the two slabs are merged in-thread, then a transposing butterfly (31 shuffles per 32x32 chunk; lane l ends with the
+//      maximum of column l over the warp's 64 rows);
+//   2. the 32 maxima go through shared memory back to every lane (one store, 8 broadcast 128-bit loads), and each lane
+//      tests its own values for equality with them; the attaining rows race with atomicMin on the row index, which is
+//      torch's first-index rule;
+//   3. after a per-tile barrier one thread per column merges the CTA's four row groups and issues one 64-bit atomicMax of
+//      (value, ~row) per column: the same packed format mnn_tc_kernel's second GEMM produced, so mnn_finalize_kernel is
+//      unchanged and the result is identical.
+// Halves the tensor-pipe work of mnn_tc_kernel, which ncu shows is the bound (80 % pipe-active, profiles/r01).
+__device__ __forceinline__ void col_butterfly(float (&a)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < o; ++j) {
+      const float keep = up ? a[j + o] : a[j];
+      const float send = up ? a[j] : a[j + o];
+      a[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC1_THREADS, 1) mnn_tc_once_kernel(const __grid_constant__ TcMaps maps,
+                                                                    const int* __restrict__ n1p, int n1_max,
+                                                                    const int* __restrict__ n2p, int n2_max, int n_pad,
+                                                                    unsigned long long* __restrict__ best12,
+                                                                    unsigned long long* __restrict__ best21) {
+  const int pair = blockIdx.y;
+  const int n_rows = n1p ? min(n1p[pair], n1_max) : n1_max;
+  const int n_cols = n2p ? min(n2p[pair], n2_max) : n2_max;
+  const int row0 = blockIdx.x * TC_ROWS;
+  if (row0 >= n_rows) return;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = base;                       // [slab 2][kb 3] boxes
+  unsigned char* sB = base + 6 * TC_BOX_BYTES;    // [stage 2][kb 3] boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 12 * TC_BOX_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;     // [2]
+  uint64_t* b_empty = bars + 3;    // [2]
+  uint64_t* acc_full = bars + 5;   // [2]
+  uint64_t* acc_empty = bars + 7;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  unsigned long long* sMerge = reinterpret_cast<unsigned long long*>(bars + 12);   // [3 column quarters][2 slabs][128 rows]
+  float* sVal = reinterpret_cast<float*>(sMerge + 3 * 256);                         // [2 tile parities][4 row groups][128 columns]
+  unsigned* sRow = reinterpret_cast<unsigned*>(sVal + 2 * 4 * 128);                 // same shape: lowest attaining row
+  unsigned* sBal = sRow + 2 * 4 * 128;                                              // [16 warps][2 slabs][32 columns] ballots
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (n_cols + TC_BN - 1) / TC_BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&maps.m1);
+    tc::tma_prefetch_desc(&maps.m2);
+    tc::mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&b_full[i], 1);
+      tc::mbar_init(&b_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], TC1_EPI_WARPS);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      // ---------------- TMA producer ----------------
+      const int arow = pair * n_pad + row0;
+      tc::mbar_expect_tx(a_full, 6 * TC_BOX_BYTES);
+      for (int slab = 0; slab < 2; ++slab)
+        for (int kb = 0; kb < 3; ++kb)
+          tc::tma_load_2d(sA + (slab * 3 + kb) * TC_BOX_BYTES, &maps.m1, a_full, kb * 64, arow + slab * 128);
+      const int brow = pair * n_pad;
+      for (int t = 0; t < T; ++t) {
+        const int s = t & 1;
+        tc::mbar_wait(&b_empty[s], ((t >> 1) & 1) ^ 1);
+        tc::mbar_expect_tx(&b_full[s], 3 * TC_BOX_BYTES);
+        for (int kb = 0; kb < 3; ++kb)
+          tc::tma_load_2d(sB + (s * 3 + kb) * TC_BOX_BYTES, &maps.m2, &b_full[s], kb * 64, brow + t * TC_BN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, TC_BN);
+      tc::mbar_wait(a_full, 0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t & 1, ph = (t >> 1) & 1;
+        tc::mbar_wait(&b_full[s], ph);
+        tc::mbar_wait(&acc_empty[s], ph ^ 1);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int slab = 0; slab < 2; ++slab) {
+          const uint32_t d = tmem + s * 256 + slab * 128;
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + (slab * 3 + kb) * TC_BOX_BYTES), 1024);
+            const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 3 + kb) * TC_BOX_BYTES), 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::umma_f16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+        }
+        tc::umma_commit(&b_empty[s]);
+        tc::umma_commit(&acc_full[s]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: running row arg-max + column arg-max ----------------
+    // 16 warps: TMEM lane quarter q = warp & 3 (hardware rule), column quarter cq = (warp - 2) >> 2 of each 128-column slab.
+    // Four warps per scheduler: the shuffle / ballot chains of one warp are latency-bound (ncu on the 8-warp version: 42 %
+    // issue-active with 1.7 "wait" stalls per issue), so thread-level parallelism is what fills the issue slots.  To fit 576
+    // threads in the register file the chunk is re-read from TMEM for the ballots instead of being kept live.
+    const int q = warp & 3, cq = (warp - 2) >> 2, et = threadIdx.x - 64;
+    float best[2] = {-INFINITY, -INFINITY};
+    uint32_t bidx[2] = {0xffffffffu, 0xffffffffu};
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const bool tail = row0 + TC_ROWS > n_rows;                 // CTA-uniform: some rows are padding
+    const bool valid0 = row0 + q * 32 + lane < n_rows, valid1 = row0 + 128 + q * 32 + lane < n_rows;
+    const uint32_t gbase = (uint32_t)(row0 + q * 32);
+    const uint32_t sbal = tc::smem_u32(sBal + (warp - 2) * 64);   // this warp's ballot scratch [2 slabs][32 columns]
+    auto reduce_chunk = [&](const uint32_t (&r)[32], int col0, int slab) {
+      if (col0 + 32 <= n_cols) {
+        float m = __uint_as_float(r[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+        if (m > best[slab]) {            // strict: earlier columns win ties (torch.max / argmax rule)
+          int j0 = 31;
+#pragma unroll
+          for (int j = 30; j >= 0; --j)
+            if (__uint_as_float(r[j]) == m) j0 = j;
+          best[slab] = m;
+          bidx[slab] = (uint32_t)(col0 + j0);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]);
+          if (col0 + j < n_cols && v > best[slab]) { best[slab] = v; bidx[slab] = (uint32_t)(col0 + j); }
+        }
+      }
+    };
+    // ballots "row attains the column maximum" for one slab of the chunk; lane `owner` parks them in shared memory
+    auto ballots = [&](const uint32_t (&r)[32], const float (&mm)[32], bool valid, uint32_t dst, int owner) {
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        unsigned b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b[k] = __ballot_sync(0xffffffffu, valid && __uint_as_float(r[4 * j4 + k]) == mm[4 * j4 + k]);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %0, %1;\n\t@p st.shared.v4.u32 [%2], {%3, %4, %5, %6};\n\t}"
+                     ::"r"(lane), "r"(owner), "r"(dst + 16 * j4), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]) : "memory");
+      }
+    };
+    for (int t = 0; t < T; ++t) {
+      const int s = t & 1, ph = (t >> 1) & 1;
+      tc::mbar_wait(&acc_full[s], ph);
+      tc::tc_fence_after();
+      uint32_t x[32], y[32];
+      const uint32_t tb = lane_addr + s * 256 + cq * 32;
+      const int cb = t * TC_BN + cq * 32;
+      const uint32_t sval = tc::smem_u32(sVal + (s * 4 + q) * 128 + cq * 32);
+      const uint32_t srow = tc::smem_u32(sRow + (s * 4 + q) * 128 + cq * 32);
+      __syncwarp();
+      tc::tmem_ld_32x32(tb, x);            // slab 0, columns cb .. cb+31
+      tc::tmem_ld_32x32(tb + 128, y);      // slab 1, same columns
+      tc::tmem_ld_wait();
+      reduce_chunk(x, cb, 0);
+      reduce_chunk(y, cb, 1);
+      // column maxima over the warp's 64 rows: merge the slabs in-thread, transpose-reduce across the lanes
+      float a[32];
+      if (!tail) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = fmaxf(__uint_as_float(x[j]), __uint_as_float(y[j]));
+      } else {                             // padding rows must not win a column
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          a[j] = fmaxf(valid0 ? __uint_as_float(x[j]) : -INFINITY, valid1 ? __uint_as_float(y[j]) : -INFINITY);
+      }
+      col_butterfly(a, lane);              // lane l now holds the maximum of column cb + l
+      __syncwarp();
+      tc::tmem_ld_32x32(tb, x);            // re-read slab 0 for the ballots (cheaper than keeping 64 registers live)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(sval + 4 * lane), "f"(a[0]) : "memory");
+      __syncwarp();
+      float mm[32];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(mm[4 * j4]), "=f"(mm[4 * j4 + 1]), "=f"(mm[4 * j4 + 2]), "=f"(mm[4 * j4 + 3])
+                     : "r"(sval + 16 * j4));   // broadcast read
+      tc::tmem_ld_wait();
+      __syncwarp();
+      tc::tmem_ld_32x32(tb + 128, y);      // slab 1 again, in flight during the slab-0 ballots
+      ballots(x, mm, valid0, sbal, 0);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[s]);   // all TMEM reads of this buffer are done
+      ballots(y, mm, valid1, sbal + 128, 1);
+      __syncwarp();
+      unsigned c0, c1;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c0) : "r"(sbal + 4 * lane));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c1) : "r"(sbal + 128 + 4 * lane));
+      // lowest attaining row of column `lane`: slab 0 rows precede slab 1 rows; lanes are rows in order
+      const uint32_t rfirst = c0 ? gbase + (uint32_t)(__ffs((int)c0) - 1) : (c1 ? gbase + 128u + (uint32_t)(__ffs((int)c1) - 1) : 0xffffffffu);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(srow + 4 * lane), "r"(rfirst) : "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // the tile's per-group column results are complete in parity s
+      if (et < 128 && t * TC_BN + et < n_cols) {
+        unsigned long long p = 0ull;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const unsigned r = sRow[(s * 4 + g) * 128 + et];
+          if (r != 0xffffffffu) {
+            const unsigned long long c = pack_vi(sVal[(s * 4 + g) * 128 + et], r);
+            p = c > p ? c : p;
+          }
+        }
+        if (p) atomicMax(best21 + (int64_t)pair * n2_max + t * TC_BN + et, p);
+      }
+      // parity s is written again for tile t+2, i.e. after the barrier of tile t+1, which these readers join afterwards
+    }
+    // merge the four column quarters of every row (lower column index wins ties through the packed compare)
+    unsigned long long pk[2];
+#pragma unroll
+    for (int slab = 0; slab < 2; ++slab) pk[slab] = (bidx[slab] == 0xffffffffu) ? 0ull : pack_vi(best[slab], bidx[slab]);
+    if (cq > 0) {
+      sMerge[(cq - 1) * 256 + 0 * 128 + q * 32 + lane] = pk[0];
+      sMerge[(cq - 1) * 256 + 1 * 128 + q * 32 + lane] = pk[1];
+    }
+    asm volatile("bar.sync 1, 512;" ::: "memory");     // epilogue warps only
+    if (cq == 0) {
+#pragma unroll
+      for (int slab = 0; slab < 2; ++slab) {
+        unsigned long long m = pk[slab];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const unsigned long long o = sMerge[c * 256 + slab * 128 + q * 32 + lane];
+          m = o > m ? o : m;
+        }
+        const int row = row0 + slab * 128 + q * 32 + lane;
+        if (row < n_rows) best12[(int64_t)pair * n1_max + row] = m;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, 512);
+  }
+}
+
 struct MnnTcWs {
   __half *f1s, *f2s;
   unsigned long long *best12, *best21;
@@ -312,7 +579,7 @@ static int make_map(CUtensorMap* m, const __half* ptr, uint64_t rows) {
 // Fills best12 (rows of F1 -> arg-max column in F2) and best21 (rows of F2 -> arg-max in F1), packed (value*s^2, index).
 int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, const float* f2, const int* n2, int n2_max,
                   int64_t stride2, int batch, void* d_ws, size_t ws_bytes, unsigned long long** best12,
-                  unsigned long long** best21, float** inv_s2, cudaStream_t st) {
+                  unsigned long long** best21, float** inv_s2, cudaStream_t st, int once) {
   Bump bump(d_ws, ws_bytes);
   MnnTcWs ws;
   carve_mnn_tc(bump, batch, n1_max, n2_max, ws);
@@ -339,16 +606,23 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
   static bool attr_done = false;
   if (!attr_done) {
     XF_CUDA(cudaFuncSetAttribute(mnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    XF_CUDA(cudaFuncSetAttribute(mnn_tc_once_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC1_SMEM));
     attr_done = true;
   }
   XF_CUDA(cudaMemsetAsync(ws.best12, 0, sizeof(unsigned long long) * (size_t)batch * n1_max, st));
+  *inv_s2 = ws.inv_s2;
+  *best12 = ws.best12;
+  *best21 = ws.best21;
   XF_CUDA(cudaMemsetAsync(ws.best21, 0, sizeof(unsigned long long) * (size_t)batch * n2_max, st));
+  if (once) {
+    dim3 grid1(n_pad / TC_ROWS, batch);
+    mnn_tc_once_kernel<<<grid1, TC1_THREADS, TC1_SMEM, st>>>(maps, n1, n1_max, n2, n2_max, n_pad, ws.best12, ws.best21);
+    XF_LAUNCH_CHECK();
+    return XF_OK;
+  }
   dim3 grid(n_pad / TC_ROWS, batch, 2);
   mnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(maps, n1, n1_max, n2, n2_max, n_pad, ws.best12, ws.best21);
   XF_LAUNCH_CHECK();
-  *best12 = ws.best12;
-  *best21 = ws.best21;
-  *inv_s2 = ws.inv_s2;
   return XF_OK;
 }
 

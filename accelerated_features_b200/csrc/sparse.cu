@@ -139,6 +139,167 @@ __global__ void __launch_bounds__(256) nms_score_kernel(const float* __restrict_
     if (gbase + i < cap) keys[(int64_t)b * cap + gbase + i] = sKeys[i];
 }
 
+// Score of one NMS survivor, packed as a sort key: nearest(K1h) * bilinear(H1) with the reference's out-of-range quirks
+// (xfeat.py:77-80); returns false when the score is not positive (`valid = scores > 0`, xfeat.py:98).
+__device__ __forceinline__ bool nms_score_key(const float* __restrict__ hb, const float* __restrict__ rb, int x, int y, float v,
+                                              int H, int W, int Hm, int Wm, unsigned long long& key) {
+  const int xn = (int)rintf(sparse_src_coord(x, W, W));
+  const int yn = (int)rintf(sparse_src_coord(y, H, H));
+  float kv = 0.f;
+  if (xn >= 0 && xn < W && yn >= 0 && yn < H) kv = (xn == x && yn == y) ? v : __ldg(hb + (int64_t)yn * W + xn);
+  const float ix = sparse_src_coord(x, W, Wm), iy = sparse_src_coord(y, H, Hm);
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+  const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+  const bool xin0 = (x0 >= 0 && x0 < Wm), xin1 = (x0 + 1 >= 0 && x0 + 1 < Wm);
+  const bool yin0 = (y0 >= 0 && y0 < Hm), yin1 = (y0 + 1 >= 0 && y0 + 1 < Hm);
+  float bil = 0.f;
+  if (xin0 && yin0) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)y0 * Wm + x0), __fmul_rn(wx0, wy0)));
+  if (xin1 && yin0) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)y0 * Wm + x0 + 1), __fmul_rn(wx1, wy0)));
+  if (xin0 && yin1) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)(y0 + 1) * Wm + x0), __fmul_rn(wx0, wy1)));
+  if (xin1 && yin1) bil = __fadd_rn(bil, __fmul_rn(__ldg(rb + (int64_t)(y0 + 1) * Wm + x0 + 1), __fmul_rn(wx1, wy1)));
+  float score = __fmul_rn(kv, bil);
+  if (x == 0 && y == 0) score = -1.f;  // indistinguishable from the zero padding rows (xfeat.py:80)
+  key = ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(y * W + x));
+  return score > 0.f;
+}
+
+// Overflow path of nms_march_kernel (CTA-local list full): score and append one survivor directly.  Not inlined: it would be
+// replicated into every unrolled row of the march and push the hot loop out of the instruction cache.
+__device__ __noinline__ void nms_emit_direct(const float* __restrict__ hb, const float* __restrict__ rb, int px, int py, float v,
+                                             int H, int W, int Hm, int Wm, unsigned long long* __restrict__ keys_b,
+                                             int* __restrict__ n_keep_b, int cap) {
+  unsigned long long key;
+  if (nms_score_key(hb, rb, px, py, v, H, W, Hm, Wm, key)) {
+    const int g = atomicAdd(n_keep_b, 1);
+    if (g < cap) keys_b[g] = key;
+  }
+}
+
+// Register-marching variant of the NMS test (default).  A warp owns a 128-pixel-wide column strip and walks down NM_RS + 4
+// rows: one 128-bit load per lane and row, the two neighbours on either side come from the adjacent lanes by shuffle, the
+// horizontal 5-max of the last five rows lives in a register ring, so the heat-map is read once (plus 4 halo rows per strip)
+// and no shared-memory tile or block barrier sits on the streaming path.  Survivors (a few per cent of the pixels) go to a
+// CTA-local list and are scored densely afterwards exactly as in nms_score_kernel; a full list degrades to direct emission.
+constexpr int NM_WARPS = 4, NM_RS = 16, NM_TW = 128, NM_LIST = 1024;
+
+__global__ void __launch_bounds__(NM_WARPS * 32, 5) nms_march_kernel(const float* __restrict__ heat, const float* __restrict__ rel,
+                                                                  int H, int W, int Hm, int Wm, float thr, int cap,
+                                                                  unsigned long long* __restrict__ keys,
+                                                                  int* __restrict__ n_keep, int* __restrict__ n_cand) {
+  __shared__ unsigned sPos[NM_LIST];
+  __shared__ float sVal[NM_LIST];
+  __shared__ unsigned long long sKeys[NM_LIST];
+  __shared__ int sCnt[3];  // [0] maxima above threshold, [1] kept (score > 0), [2] global base
+  const int b = blockIdx.z, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* hb = heat + (int64_t)b * H * W;
+  const float* rb = rel + (int64_t)b * Hm * Wm;
+  if (threadIdx.x < 3) sCnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int x = blockIdx.x * NM_TW + lane * 4;
+  const int y0 = (blockIdx.y * NM_WARPS + warp) * NM_RS;
+  const bool xin = x < W;   // W % 4 == 0: a lane's four pixels are inside or outside together
+  if (y0 < H) {
+    float hr[5][4];   // horizontal 5-max of the last five rows
+    float vc[5][4];   // centre values of the last five rows (same period as hr, so every batch of NB = 5 rows is the same code)
+    constexpr int NB = 5;   // rows loaded per batch: all loads of a batch are issued before the first is consumed
+    static_assert((NM_RS + 4) % NB == 0, "march length must be a multiple of the load batch");
+#pragma unroll 1   // rolled: the fully unrolled march (20 rows) stalled on instruction fetch (ncu: no_instruction 3.0 per issue)
+    for (int i0 = 0; i0 < NM_RS + 4; i0 += NB) {
+    float4 vb[NB];
+    float2 eb[NB];   // lane 0: pixels x-2, x-1; lane 31: pixels x+4, x+5 (the neighbours no other lane of the warp holds)
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int y = y0 - 2 + i0 + u;
+      const bool yin = y >= 0 && y < H;
+      const float* row = hb + (int64_t)(yin ? y : 0) * W;
+      vb[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);   // MaxPool2d pads with -inf
+      eb[u] = make_float2(-INFINITY, -INFINITY);
+      if (yin && xin) vb[u] = __ldg(reinterpret_cast<const float4*>(row + x));
+      if (yin && xin && lane == 0 && x > 0) eb[u] = __ldg(reinterpret_cast<const float2*>(row + x - 2));
+      if (yin && lane == 31 && x + 4 < W) eb[u] = __ldg(reinterpret_cast<const float2*>(row + x + 4));
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int i = i0 + u;
+      const int y = y0 - 2 + i;
+      const float4 v = vb[u];
+      float l1 = __shfl_up_sync(0xffffffffu, v.w, 1);
+      float l2 = __shfl_up_sync(0xffffffffu, v.z, 1);
+      float r1 = __shfl_down_sync(0xffffffffu, v.x, 1);
+      float r2 = __shfl_down_sync(0xffffffffu, v.y, 1);
+      if (lane == 0) { l2 = eb[u].x; l1 = eb[u].y; }
+      if (lane == 31) { r1 = eb[u].x; r2 = eb[u].y; }
+      const float mxyz = fmaxf(fmaxf(v.x, v.y), v.z), myzw = fmaxf(fmaxf(v.y, v.z), v.w);
+      hr[u][0] = fmaxf(fmaxf(l2, l1), mxyz);
+      hr[u][1] = fmaxf(fmaxf(l1, v.w), mxyz);
+      hr[u][2] = fmaxf(fmaxf(v.x, r1), myzw);
+      hr[u][3] = fmaxf(fmaxf(r1, r2), myzw);
+      vc[u][0] = v.x; vc[u][1] = v.y; vc[u][2] = v.z; vc[u][3] = v.w;
+      if (i >= 4) {
+        const int yo = y - 2;   // output row: window rows yo-2 .. yo+2 are in the ring
+        unsigned mask = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float m = fmaxf(fmaxf(fmaxf(hr[0][k], hr[1][k]), fmaxf(hr[2][k], hr[3][k])), hr[4][k]);
+          const float c = vc[(u + 3) % 5][k];
+          if (c == m && c > thr) mask |= 1u << k;
+        }
+        if (!(xin && yo < H)) mask = 0;
+        if (mask) {
+          int e = atomicAdd(&sCnt[0], __popc(mask));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (mask & (1u << k)) {
+              const float c = vc[(u + 3) % 5][k];
+              if (e < NM_LIST) {
+                sPos[e] = (uint32_t)(yo * W + x + k);
+                sVal[e] = c;
+              } else {
+                nms_emit_direct(hb, rb, x + k, yo, c, H, W, Hm, Wm, keys + (int64_t)b * cap, n_keep + b, cap);
+              }
+              ++e;
+            }
+        }
+      }
+    }
+    }
+  }
+  __syncthreads();
+  // ---- score the survivors densely, compact the positive scores ----
+  const int nc_all = sCnt[0];
+  const int nc = nc_all < NM_LIST ? nc_all : NM_LIST;
+  for (int i0 = 0; i0 < nc; i0 += NM_WARPS * 32) {
+    const int i = i0 + threadIdx.x;
+    bool keep = false;
+    unsigned long long key = 0;
+    if (i < nc) {
+      const int pix = (int)sPos[i];
+      const int py = pix / W, px = pix - py * W;
+      keep = nms_score_key(hb, rb, px, py, sVal[i], H, W, Hm, Wm, key);
+    }
+    const unsigned mkeep = __ballot_sync(0xffffffffu, keep);
+    if (mkeep) {
+      const int leader = __ffs(mkeep) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&sCnt[1], __popc(mkeep));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (keep) sKeys[base + __popc(mkeep & ((1u << lane) - 1u))] = key;
+    }
+  }
+  __syncthreads();
+  const int nk = sCnt[1];
+  if (threadIdx.x == 0) {
+    if (nc_all) atomicAdd(&n_cand[b], nc_all);
+    sCnt[2] = nk ? atomicAdd(&n_keep[b], nk) : 0;
+  }
+  __syncthreads();
+  const int gbase = sCnt[2];
+  for (int i = threadIdx.x; i < nk; i += NM_WARPS * 32)
+    if (gbase + i < cap) keys[(int64_t)b * cap + gbase + i] = sKeys[i];
+}
+
 __global__ void segment_offsets_kernel(const int* __restrict__ counts, int cap, int B, int* __restrict__ begin,
                                        int* __restrict__ end) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,6 +423,7 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
 // the keypoints are then processed in that (spatial) order, so the 4x4x256 B tap blocks of neighbouring keypoints hit
 // L1 instead of L2 (5x5 NMS puts keypoints >= 3 px apart while a feature cell covers 8 px).  Results go to the slot given
 // by the score rank, exactly as in the generic kernel.
+// (Sharing an image between 4 CTAs of 512 threads, each repeating the bucketing, measured 321 us vs 268 us: not kept.)
 constexpr int SAMPLE_MAX_K = 8192, SAMPLE_THREADS = 1024, SAMPLE_MAX_ROWS = 512;
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
     const unsigned long long* __restrict__ sorted, const int* __restrict__ n_keep, const float* __restrict__ feats,
@@ -405,9 +567,16 @@ extern "C" int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const f
   const int cap = xf::sparse_cap(H, W), Hm = H / 8, Wm = W / 8;
   XF_CUDA(cudaMemsetAsync(ws.n_keep, 0, sizeof(int) * B, st));
   XF_CUDA(cudaMemsetAsync(ws.n_cand, 0, sizeof(int) * B, st));
-  dim3 grid(xf::cdiv(W, xf::NMS_TX), xf::cdiv(H, xf::NMS_TY), B);
-  xf::nms_score_kernel<<<grid, 256, 0, st>>>(d_heat, d_reliability, H, W, Hm, Wm, threshold, cap, ws.keys, ws.n_keep,
-                                             ws.n_cand);
+  static const bool nms_tiled = getenv("XFEAT_NMS_TILED") != nullptr;   // A/B switch: the shared-memory tile kernel
+  if (nms_tiled || (W & 3)) {
+    dim3 grid(xf::cdiv(W, xf::NMS_TX), xf::cdiv(H, xf::NMS_TY), B);
+    xf::nms_score_kernel<<<grid, 256, 0, st>>>(d_heat, d_reliability, H, W, Hm, Wm, threshold, cap, ws.keys, ws.n_keep,
+                                               ws.n_cand);
+  } else {
+    dim3 grid(xf::cdiv(W, xf::NM_TW), xf::cdiv(H, xf::NM_WARPS * xf::NM_RS), B);
+    xf::nms_march_kernel<<<grid, xf::NM_WARPS * 32, 0, st>>>(d_heat, d_reliability, H, W, Hm, Wm, threshold, cap, ws.keys,
+                                                             ws.n_keep, ws.n_cand);
+  }
   XF_LAUNCH_CHECK();
   xf::segment_offsets_kernel<<<xf::cdiv(B, 128), 128, 0, st>>>(ws.n_keep, cap, B, ws.seg_begin, ws.seg_end);
   XF_LAUNCH_CHECK();

@@ -148,6 +148,97 @@ static int launch_stem(const float* hw, const float* hb, const float* sw, const 
   return XF_OK;
 }
 
+// block1.0 + block1.1 in one pass (tensor-core schedule): a thread produces a 2x2 patch of the half-resolution, 8-channel
+// block1.1 output.  It needs the 5x5 full-resolution block1.0 pixels around it, which it recomputes from a 7x7 window of the
+// gray image held in registers, so the (B,H,W,4) fp32 intermediate (630 MB written + read per 128 VGA images) never exists.
+// FMA order per output equals stem_conv_kernel's (taps row-major, then input channel), so both schedules agree bit for bit.
+struct Stem01W {
+  float w0[9 * 4];      // block1.0 [tap][cout4]
+  float b0[4];
+  float w1[9 * 4 * 8];  // block1.1 [tap][cin4][cout8]
+  float b1[8];
+};
+
+__global__ void __launch_bounds__(128) stem01_kernel(const __grid_constant__ Stem01W P, const float* __restrict__ xn,
+                                                     __half* __restrict__ out_split8, int H, int W) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int ox0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 2;
+  const int oy0 = (blockIdx.y * 4 + (threadIdx.x >> 5)) * 2;
+  const int b = blockIdx.z;
+  if (ox0 >= Wo || oy0 >= Ho) return;
+  const float* xb = xn + (int64_t)b * H * W;
+  const int gy0 = 2 * oy0 - 2, gx0 = 2 * ox0 - 2;   // top-left of the 7x7 gray window
+  float g[7][7];
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const int y = gy0 + r;
+    const bool yin = y >= 0 && y < H;
+    const float* row = xb + (int64_t)(yin ? y : 0) * W;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      const int x = gx0 + c;
+      g[r][c] = (yin && x >= 0 && x < W) ? __ldg(row + x) : 0.f;
+    }
+  }
+  float acc[2][2][8];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) (&acc[0][0][0])[i] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const int ay = 2 * oy0 - 1 + r;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const int ax = 2 * ox0 - 1 + c;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) a[ch] = fmaf(g[r + ky][c + kx], P.w0[(ky * 3 + kx) * 4 + ch], a[ch]);
+      const bool ain = ay >= 0 && ay < H && ax >= 0 && ax < W;   // outside the image block1.1 sees zero padding
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) a[ch] = ain ? fmaxf(a[ch] + P.b0[ch], 0.f) : 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int ky = r - 2 * dy;
+        if (ky < 0 || ky > 2) continue;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int kx = c - 2 * dx;
+          if (kx < 0 || kx > 2) continue;
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+            for (int co = 0; co < 8; ++co)
+              acc[dy][dx][co] = fmaf(a[ci], P.w1[((ky * 3 + kx) * 4 + ci) * 8 + co], acc[dy][dx][co]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    uint4* sp = reinterpret_cast<uint4*>(out_split8 + (((int64_t)b * Ho + oy0 + dy) * Wo + ox0) * 16);
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v0 = fmaxf(acc[dy][dx][2 * j] + P.b1[2 * j], 0.f), v1 = fmaxf(acc[dy][dx][2 * j + 1] + P.b1[2 * j + 1], 0.f);
+        const __half2 h = __floats2half2_rn(v0, v1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+        hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      sp[2 * dx] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      sp[2 * dx + 1] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  }
+}
+
+static int g_stem_fused = 1;   // XFEAT_STEM_UNFUSED=1 in the environment selects the two-kernel path (A/B measurements)
+
 // xn (B,H,W) -> a1 (B,H,W,4) -> a2 (B,H/2,W/2,8) -> a3 (same,8) -> x1s (B,H/4,W/4,24) = block1(x) + skip1(x)
 // tc_tail != 0: only block1.0 and block1.1 run here (block1.1 writes split fp16 [hi8|lo8] into a2); block1.2 / block1.3 + skip
 // continue on the tensor cores (api.cu).
@@ -155,6 +246,19 @@ int launch_stem_chain(const float* h_weights, const LayerTable& t, const float* 
                       float* x1s, __half* x1s_split32, int B, int H, int W, cudaStream_t st, int tc_tail) {
   const float* hw = h_weights;
   int rc;
+  static const bool unfused = getenv("XFEAT_STEM_UNFUSED") != nullptr;
+  if (tc_tail && g_stem_fused && !unfused) {
+    Stem01W P;
+    memcpy(P.w0, hw + t.w_off[L_B1_0], sizeof(P.w0));
+    memcpy(P.b0, hw + t.b_off[L_B1_0], sizeof(P.b0));
+    memcpy(P.w1, hw + t.w_off[L_B1_1], sizeof(P.w1));
+    memcpy(P.b1, hw + t.b_off[L_B1_1], sizeof(P.b1));
+    dim3 grid(cdiv(W / 4, 32), cdiv(H / 4, 4), B);
+    // (capping registers at 128 for 4 CTAs/SM measured the same 333 us as 158 registers / 3 CTAs: issue-bound, not latency-bound)
+    stem01_kernel<<<grid, 128, 0, st>>>(P, xn, (__half*)a2, H, W);
+    XF_LAUNCH_CHECK();
+    return XF_OK;
+  }
   rc = launch_stem<1, 4, 1, false>(hw + t.w_off[L_B1_0], hw + t.b_off[L_B1_0], nullptr, nullptr, xn, nullptr, a1, nullptr, B, H, W, st);
   if (rc) return rc;
   rc = launch_stem<4, 8, 2, false>(hw + t.w_off[L_B1_1], hw + t.b_off[L_B1_1], nullptr, nullptr, a1, nullptr, a2,

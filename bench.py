@@ -290,15 +290,19 @@ def run_gpu(args):
         flops = 2.0 * 64.0 * float((out[3].double() * out[4].double()).sum())
         achieved = flops / (mnn_ms / 1e3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        tc = lib.xfeat_get_mnn_impl() == 1
-        kname = ("mnn_tc_kernel (tcgen05 split-fp16 K=192 D1.D2^T, fp32 accumulate in TMEM, fused row arg-max, both directions; "
+        tc = lib.xfeat_get_mnn_impl() >= 1
+        kname = ("mnn_tc_once_kernel (tcgen05 split-fp16 K=192 D1.D2^T, fp32 accumulate in TMEM, fused row + column arg-max; "
                  "timed call also contains absmax/split/finalize)") if tc else "mnn_scan_kernel (fp32 FFMA D1.D2^T + fused row/col arg-max)"
         ncu = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01", "ncu_mnn_tc_final.json")) as f:
-                ncu = json.load(f)
-        except Exception:
-            pass
+        for name in ("ncu_mnn_tc_once.json", "ncu_mnn_tc_final.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", "r01", name)) as f:
+                    ncu = json.load(f)
+                if (ncu.get("kernel") == "mnn_tc_once_kernel") == (lib.xfeat_get_mnn_impl() == 2):
+                    break
+                ncu = None
+            except Exception:
+                pass
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

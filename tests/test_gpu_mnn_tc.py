@@ -55,22 +55,27 @@ def run(xf, f1, f2, thr):
     return i0.cpu().numpy(), i1.cpu().numpy()
 
 
-def test_tc_golden(xf, golden):
+TC_IMPLS = [1, 2]   # 1: one GEMM per direction, 2: single pass (row arg-max + column maxima from one accumulator tile)
+
+
+@pytest.mark.parametrize("impl", TC_IMPLS)
+def test_tc_golden(xf, golden, impl):
     g = golden("g5_mnn.npz")
     f1, f2 = torch.from_numpy(g["f1"]), torch.from_numpy(g["f2"])
-    with mnn_impl(xf, 1):
+    with mnn_impl(xf, impl):
         for thr, sfx in ((-1, ""), (0.82, "_082"), (0.3, "_03")):
             got = run(xf, f1, f2, thr)
             nd = check_modulo_ties(f1, f2, got, (g["idx0" + sfx], g["idx1" + sfx]))
             print(f"thr={thr}: {len(got[0])} matches, {nd} tie-differences")
 
 
+@pytest.mark.parametrize("impl", TC_IMPLS)
 @pytest.mark.parametrize("n1,n2", [(1, 1), (5, 300), (129, 127), (256, 256), (257, 511), (1000, 2048), (4096, 4096), (2500, 777)])
-def test_tc_vs_oracle_sizes(xf, n1, n2):
+def test_tc_vs_oracle_sizes(xf, n1, n2, impl):
     g = torch.Generator().manual_seed(n1 * 7 + n2)
     f1 = F.normalize(torch.randn(n1, 64, generator=g), dim=-1)
     f2 = F.normalize(torch.randn(n2, 64, generator=g), dim=-1)
-    with mnn_impl(xf, 1):
+    with mnn_impl(xf, impl):
         for thr in (-1, 0.3):
             w0, w1 = orc.mnn_match(f1, f2, thr)
             got = run(xf, f1, f2, thr)
@@ -78,7 +83,8 @@ def test_tc_vs_oracle_sizes(xf, n1, n2):
             assert nd <= max(2, n1 // 500)
 
 
-def test_tc_equals_simt_on_real_descriptors(xf, assets_vga):
+@pytest.mark.parametrize("impl", TC_IMPLS)
+def test_tc_equals_simt_on_real_descriptors(xf, assets_vga, impl):
     """Descriptors of the asset pair: both implementations must return the same matches (modulo near-ties)."""
     ref, tgt = assets_vga
     out = xf.detectAndCompute(np.stack([ref, tgt]).transpose(0, 3, 1, 2).astype(np.float32) / 255, top_k=4096) \
@@ -86,7 +92,7 @@ def test_tc_equals_simt_on_real_descriptors(xf, assets_vga):
     d0, d1 = out[0]["descriptors"], out[1]["descriptors"]
     with mnn_impl(xf, 0):
         a0, a1 = xf.match(d0, d1, -1)
-    with mnn_impl(xf, 1):
+    with mnn_impl(xf, impl):
         b0, b1 = xf.match(d0, d1, -1)
         c0, c1 = xf.match(d0, d1, 0.82)
     nd = check_modulo_ties(d0.cpu(), d1.cpu(), (b0.cpu().numpy(), b1.cpu().numpy()), (a0.cpu().numpy(), a1.cpu().numpy()))
@@ -96,14 +102,15 @@ def test_tc_equals_simt_on_real_descriptors(xf, assets_vga):
     assert nd <= 4
 
 
-def test_tc_batched_ragged_unnormalised(xf):
+@pytest.mark.parametrize("impl", TC_IMPLS)
+def test_tc_batched_ragged_unnormalised(xf, impl):
     g = torch.Generator().manual_seed(11)
     B, N = 5, 700
     f1 = torch.randn(B, N, 64, generator=g) * 3.0
     f2 = torch.randn(B, N, 64, generator=g) * 3.0
     n1 = [700, 1, 128, 333, 0]
     n2 = [700, 700, 129, 5, 40]
-    with mnn_impl(xf, 1):
+    with mnn_impl(xf, impl):
         idx0, idx1, cnt = xf._mnn_device(f1.cuda(), torch.tensor(n1, dtype=torch.int32).cuda(), N, N * 64, f2.cuda(),
                                          torch.tensor(n2, dtype=torch.int32).cuda(), N, N * 64, B, -1)
     c = cnt.tolist()
@@ -116,11 +123,31 @@ def test_tc_batched_ragged_unnormalised(xf):
                           (w0.numpy(), w1.numpy()))
 
 
-def test_tc_full_size_identity(xf):
+@pytest.mark.parametrize("impl", TC_IMPLS)
+def test_tc_full_size_identity(xf, impl):
     """64 x (4096 x 4096): matching a set against itself returns the identity (size-independent property)."""
     g = torch.Generator().manual_seed(5)
     f = F.normalize(torch.randn(64, 4096, 64, generator=g), dim=-1).cuda()
-    with mnn_impl(xf, 1):
+    with mnn_impl(xf, impl):
         idx0, idx1, cnt = xf._mnn_device(f, None, 4096, 4096 * 64, f, None, 4096, 4096 * 64, 64, -1)
     assert cnt.tolist() == [4096] * 64
     assert torch.equal(idx0, idx1) and torch.equal(idx0[3], torch.arange(4096, device="cuda"))
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2])
+def test_exact_ties_first_index(xf, impl):
+    """Duplicate descriptors give bit-equal similarities: torch's first-index rule decides (xfeat.py:333-339).  Rows 3/700
+    of set 1 and rows 10/450 of set 2 are duplicated; values are small integers / 8 so every product and sum is exact in
+    every implementation and the oracle comparison is bit for bit."""
+    g = torch.Generator().manual_seed(21)
+    f1 = torch.randint(-4, 5, (900, 64), generator=g).float() / 8
+    f2 = torch.randint(-4, 5, (600, 64), generator=g).float() / 8
+    f2[:300] = f1[:300]            # guaranteed strong matches
+    f1[700] = f1[3]
+    f1[701] = f1[3]
+    f2[450] = f2[10]
+    w0, w1 = orc.mnn_match(f1, f2, -1)
+    with mnn_impl(xf, impl):
+        g0, g1 = run(xf, f1, f2, -1)
+    assert np.array_equal(g0, w0.numpy()) and np.array_equal(g1, w1.numpy())
+    assert 3 in g0 and 700 not in g0 and 701 not in g0

@@ -60,7 +60,7 @@ for n in (2048, 4096, 8192, 16384, 32768):
     f1 = F.normalize(torch.randn(n, 64, generator=gen), dim=-1).cuda()
     f2 = F.normalize(torch.randn(n, 64, generator=gen), dim=-1).cuda()
     row = {"n": n}
-    for impl, name in ((1, "tcgen05"), (0, "fp32_simt")):
+    for impl, name in ((2, "tcgen05"), (1, "tcgen05_two_gemm"), (0, "fp32_simt")):
         xf._lib.xfeat_set_mnn_impl(impl)
         ms = timed(lambda: xf._mnn_device(f1, None, n, 0, f2, None, n, 0, 1, -1), n=10, warm=3)
         flops = 2.0 * n * n * 64
@@ -71,7 +71,7 @@ for n in (2048, 4096, 8192, 16384, 32768):
     idx0, idx1, cnt = xf._mnn_device(f1, None, n, 0, f2, None, n, 0, 1, -1)
     row["mutual_matches"] = int(cnt.item())
     sweep.append(row)
-xf._lib.xfeat_set_mnn_impl(1)
+xf._lib.xfeat_set_mnn_impl(2)
 out["C5_mnn_sweep"] = {"rows": sweep, "note": "single pair per call (a 32k x 32k pair fills the GPU; small N under-fills 148 SMs); "
                        "reference-equivalent GB/s = bytes the reference's materialised S (written + read) would move / our time; "
                        f"HBM copy peak {peaks['hbm_gbs']} GB/s"}
