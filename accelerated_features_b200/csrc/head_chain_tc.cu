@@ -15,7 +15,7 @@
 
 namespace xf {
 
-constexpr int HC_THREADS = 192;
+constexpr int HC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of slot 0, warps 6-9 epilogue of slot 1
 constexpr int HC_ABOX = 128 * 128;
 constexpr int HC_WBOX = 64 * 128;
 
@@ -137,18 +137,22 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
     const int r = q * 32 + lane;                             // pixel row of the tile = TMEM lane
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    uint32_t g[2] = {0, 0};
+    // One epilogue group (4 warps = the 4 TMEM lane quarters) per slot: both slots' conversions run concurrently.  With a
+    // single group serving both slots the kernel was epilogue-latency bound (ncu: issue slots 24 % active, tensor pipe 12 %).
+    const int s = (warp - 2) >> 2;
+    uint32_t gcount = 0;   // GEMMs of this slot consumed so far
     for (int i0 = 0; i0 < my_tiles; i0 += 2) {
-      const int ns = (i0 + 1 < my_tiles) ? 2 : 1;
+      if (i0 + s >= my_tiles) break;
      for (int l = 0; l <= NH; ++l) {
-      for (int s = 0; s < ns; g[s] += 1, ++s) {
+      {
         const int tile = (int)blockIdx.x + (i0 + s) * (int)gridDim.x;
         unsigned char* a_hi = sA + (size_t)s * 2 * HC_ABOX;
         unsigned char* a_lo = a_hi + HC_ABOX;
         const int64_t pix = (int64_t)tile * 128 + r;
         const uint32_t lane_addr = lane_base + s * 128;
         uint64_t* const a_ready_s = &a_ready[s];
-        tc::mbar_wait(&acc_full[s], g[s] & 1);
+        tc::mbar_wait(&acc_full[s], gcount & 1);
+        gcount += 1;
         tc::tc_fence_after();
         if (l < NH) {
           // ---- hidden layer: bias + ReLU, re-split, write the next A operand (128B swizzle: chunk j of row r at j ^ (r & 7)) ----
