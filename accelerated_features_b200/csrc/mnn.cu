@@ -209,12 +209,13 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
                   unsigned long long** best21, float** inv_s2, cudaStream_t st, int once);
 // 0 = fp32 CUDA cores, 1 = tcgen05 split-fp16 with one GEMM per direction (default), 2 = tcgen05 single pass: one GEMM, the
 // column arg-max by cross-lane reduction in the epilogue -- same results, but the epilogue then out-weighs the saved GEMM
-// (64 x 4096 x 4096: 0.80 ms vs 0.68 ms per call, tools/mnn_ab.py), so it is kept selectable, not default
+// (64 x 4096 x 4096: 0.75 ms vs 0.68 ms per call, tools/mnn_ab.py), so it is kept selectable, not default;
+// 3 = implementation 1 on CTA pairs (tcgen05 cta_group::2, M = 256 across two SMs, half the B tile per SM)
 static int g_mnn_impl = 1;
 
 }  // namespace xf
 
-extern "C" void xfeat_set_mnn_impl(int impl) { xf::g_mnn_impl = impl < 0 ? 0 : (impl > 2 ? 2 : impl); }
+extern "C" void xfeat_set_mnn_impl(int impl) { xf::g_mnn_impl = impl < 0 ? 0 : (impl > 3 ? 3 : impl); }
 extern "C" int xfeat_get_mnn_impl(void) { return xf::g_mnn_impl; }
 
 extern "C" size_t xfeat_mnn_workspace_bytes(int batch, int n1_max, int n2_max) {
@@ -238,7 +239,7 @@ extern "C" int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_ma
     unsigned long long *b12 = nullptr, *b21 = nullptr;
     float* inv_s2 = nullptr;
     int rc = xf::launch_mnn_tc(d_f1, d_n1, n1_max, stride1, d_f2, d_n2, n2_max, stride2, batch, d_ws, ws_bytes, &b12, &b21,
-                               &inv_s2, st, xf::g_mnn_impl == 2);
+                               &inv_s2, st, xf::g_mnn_impl == 2 ? 1 : (xf::g_mnn_impl == 3 ? 2 : 0));
     if (rc) return rc;
     xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(b12, b21, d_n1, n1_max, n2_max, min_cossim, inv_s2, (long long*)d_idx0,
                                                     (long long*)d_idx1, d_n_matches);

@@ -532,13 +532,212 @@ __global__ void __launch_bounds__(TC1_THREADS, 1) mnn_tc_once_kernel(const __gri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant of mnn_tc_kernel (tcgen05 cta_group::2): a cluster of two CTAs = 512 rows.  The leader CTA issues UMMAs
+// with M = 256 (its 128-row slab + the peer's) and N = 256; each CTA stages HALF of every 256-column B tile (128 rows), so
+// the shared-memory operand traffic per SM is A + B/2 = 8 KB per 128-cycle MMA = 64 B/clk, half of the single-CTA kernel's
+// (A + B = 8 KB per 64-cycle MMA at N = 128, i.e. the full 128 B/clk of shared memory).  (With N = 128 per pair-MMA the
+// variant measured slower than the single-CTA kernel, 0.77 vs 0.68 ms per call.)
+// TMEM: 2 slabs x 256 columns = all 512 columns, single-buffered per slab: the epilogue of slab 0 runs under the MMAs of
+// slab 1 and vice versa, so the accumulators are still double-buffered in time.
+// Barrier topology: operand-full barriers live in the leader and collect the TMA bytes of both CTAs; stage-empty and
+// accumulator-full barriers are per CTA and are signalled by multicast tcgen05.commit; accumulator-empty lives in the leader
+// and counts the epilogue warps of both CTAs (remote mbarrier.arrive through mapa).
+constexpr int TC2_BN = 256;
+constexpr size_t TC2_SMEM = 1024 + 12 * (size_t)TC_BOX_BYTES + 256 + 2 * 128 * 8;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    mnn_tc2_kernel(const __grid_constant__ TcMaps maps, const int* __restrict__ n1p, int n1_max, const int* __restrict__ n2p,
+                   int n2_max, int n_pad, unsigned long long* __restrict__ best12, unsigned long long* __restrict__ best21) {
+  const int pair = blockIdx.y, dir = blockIdx.z;
+  const int n1 = n1p ? min(n1p[pair], n1_max) : n1_max;
+  const int n2 = n2p ? min(n2p[pair], n2_max) : n2_max;
+  const int n_rows = dir ? n2 : n1, n_cols = dir ? n1 : n2;
+  const int out_stride = dir ? n2_max : n1_max;
+  unsigned long long* out = dir ? best21 : best12;
+  const CUtensorMap* mapA = dir ? &maps.m2 : &maps.m1;
+  const CUtensorMap* mapB = dir ? &maps.m1 : &maps.m2;
+  const int row0 = blockIdx.x * TC_ROWS;
+  if ((int)(blockIdx.x & ~1u) * TC_ROWS >= n_rows) return;   // cluster-uniform: both CTAs of the pair leave together
+  const uint32_t rank = tc::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = base;                       // [slab 2][kb 3] 128-row boxes
+  unsigned char* sB = base + 6 * TC_BOX_BYTES;    // [stage 2][kb 3] 128-row boxes = this CTA's half of a 256-column tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 12 * TC_BOX_BYTES);
+  uint64_t* a_full = bars;         // leader: A slabs of both CTAs landed
+  uint64_t* b_full = bars + 1;     // [2 stages] leader: both halves of the B stage landed
+  uint64_t* b_empty = bars + 3;    // [2 stages] per CTA (multicast commit)
+  uint64_t* acc_full = bars + 5;   // [2 slabs] per CTA (multicast commit)
+  uint64_t* acc_empty = bars + 7;  // [2 slabs] leader: 8 epilogue warps x 2 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  unsigned long long* sMerge = reinterpret_cast<unsigned long long*>(bars + 12);   // [2 slabs][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = (n_cols + TC2_BN - 1) / TC2_BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(mapA);
+    tc::tma_prefetch_desc(mapB);
+    tc::mbar_init(a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&b_full[i], 1);
+      tc::mbar_init(&b_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 16);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc_2sm(tmem_slot, 512);
+    tc::tmem_relinquish_2sm();
+  }
+  tc::tc_fence_before();
+  tc::cluster_sync();              // barrier inits + TMEM allocation of both CTAs visible before any remote signal
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      // ---------------- TMA producer (both CTAs; bytes are reported to the leader's barriers) ----------------
+      const uint32_t a_full_l = tc::mapa_rank(tc::smem_u32(a_full), 0);
+      const int arow = pair * n_pad + row0;
+      if (leader) tc::mbar_expect_tx(a_full, 2 * 6 * TC_BOX_BYTES);
+      for (int slab = 0; slab < 2; ++slab)
+        for (int kb = 0; kb < 3; ++kb)
+          tc::tma_load_2d_2sm(sA + (slab * 3 + kb) * TC_BOX_BYTES, mapA, a_full_l, kb * 64, arow + slab * 128);
+      const int brow = pair * n_pad + (int)rank * 128;   // this CTA's half of every 256-row B tile
+      for (int t = 0; t < T; ++t) {
+        const int s = t & 1;
+        tc::mbar_wait(&b_empty[s], ((t >> 1) & 1) ^ 1);
+        if (leader) tc::mbar_expect_tx(&b_full[s], 2 * 3 * TC_BOX_BYTES);
+        const uint32_t b_full_l = tc::mapa_rank(tc::smem_u32(&b_full[s]), 0);
+        for (int kb = 0; kb < 3; ++kb)
+          tc::tma_load_2d_2sm(sB + (s * 3 + kb) * TC_BOX_BYTES, mapB, b_full_l, kb * 64, brow + t * TC2_BN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && tc::elect_one()) {
+      // ---------------- MMA issuer (leader only): M = 256 across the pair, N = 256 ----------------
+      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 256, TC2_BN);
+      tc::mbar_wait_cluster(a_full, 0);
+      for (int t = 0; t < T; ++t) {
+        const int s = t & 1;
+        tc::mbar_wait_cluster(&b_full[s], (t >> 1) & 1);
+#pragma unroll
+        for (int slab = 0; slab < 2; ++slab) {
+          tc::mbar_wait_cluster(&acc_empty[slab], (t & 1) ^ 1);   // both CTAs drained this slab's accumulator (tile t-1)
+          tc::tc_fence_after();
+          const uint32_t d = tmem + slab * TC2_BN;
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + (slab * 3 + kb) * TC_BOX_BYTES), 1024);
+            const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 3 + kb) * TC_BOX_BYTES), 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma_f16_2sm(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          tc::umma_commit_2sm(&acc_full[slab], 3);   // both CTAs' accumulators of (tile t, slab) are complete
+        }
+        tc::umma_commit_2sm(&b_empty[s], 3);         // both CTAs may refill their half of the stage
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue (both CTAs, own TMEM rows): running row arg-max ----------------
+    // warps 2-9: TMEM lane quarter q = warp & 3, column half hc = (warp - 2) >> 2 (128 of the slab's 256 columns)
+    const int q = warp & 3, hc = (warp - 2) >> 2;
+    float best[2] = {-INFINITY, -INFINITY};
+    uint32_t bidx[2] = {0xffffffffu, 0xffffffffu};
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    auto reduce_chunk = [&](const uint32_t (&r)[32], int col0, int slab) {
+      if (col0 + 32 <= n_cols) {
+        float m = __uint_as_float(r[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+        if (m > best[slab]) {            // strict: earlier columns win ties (torch.max / argmax rule)
+          int j0 = 31;
+#pragma unroll
+          for (int j = 30; j >= 0; --j)
+            if (__uint_as_float(r[j]) == m) j0 = j;
+          best[slab] = m;
+          bidx[slab] = (uint32_t)(col0 + j0);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]);
+          if (col0 + j < n_cols && v > best[slab]) { best[slab] = v; bidx[slab] = (uint32_t)(col0 + j); }
+        }
+      }
+    };
+    uint32_t acc_empty_l[2];
+    acc_empty_l[0] = tc::mapa_rank(tc::smem_u32(&acc_empty[0]), 0);
+    acc_empty_l[1] = tc::mapa_rank(tc::smem_u32(&acc_empty[1]), 0);
+    for (int t = 0; t < T; ++t) {
+#pragma unroll
+      for (int slab = 0; slab < 2; ++slab) {
+        tc::mbar_wait(&acc_full[slab], t & 1);
+        tc::tc_fence_after();
+        uint32_t ra[32], rb[32];
+        const uint32_t tb = lane_addr + slab * TC2_BN + hc * 128;
+        const int cb = t * TC2_BN + hc * 128;
+        __syncwarp();
+        tc::tmem_ld_32x32(tb, ra);
+        tc::tmem_ld_wait();
+        __syncwarp();
+        tc::tmem_ld_32x32(tb + 32, rb);
+        reduce_chunk(ra, cb, slab);
+        tc::tmem_ld_wait();
+        __syncwarp();
+        tc::tmem_ld_32x32(tb + 64, ra);
+        reduce_chunk(rb, cb + 32, slab);
+        tc::tmem_ld_wait();
+        __syncwarp();
+        tc::tmem_ld_32x32(tb + 96, rb);
+        reduce_chunk(ra, cb + 64, slab);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive_cluster(acc_empty_l[slab]);   // leader's barrier: this slab may be overwritten
+        reduce_chunk(rb, cb + 96, slab);
+      }
+    }
+    unsigned long long pk[2];
+#pragma unroll
+    for (int slab = 0; slab < 2; ++slab) pk[slab] = (bidx[slab] == 0xffffffffu) ? 0ull : pack_vi(best[slab], bidx[slab]);
+    if (hc == 1) {
+      sMerge[0 * 128 + q * 32 + lane] = pk[0];
+      sMerge[1 * 128 + q * 32 + lane] = pk[1];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
+    if (hc == 0) {
+#pragma unroll
+      for (int slab = 0; slab < 2; ++slab) {
+        const unsigned long long o = sMerge[slab * 128 + q * 32 + lane];
+        const unsigned long long m = o > pk[slab] ? o : pk[slab];
+        const int row = row0 + slab * 128 + q * 32 + lane;
+        if (row < n_rows) out[(int64_t)pair * out_stride + row] = m;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  tc::cluster_sync();              // the peer's shared memory / TMEM must outlive the leader's last MMA
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc_2sm(tmem, 512);
+  }
+}
+
 struct MnnTcWs {
   __half *f1s, *f2s;
   unsigned long long *best12, *best21;
   unsigned* absmax;
   float* inv_s2;
 };
-static inline int tc_pad(int n) { return (n + TC_ROWS - 1) / TC_ROWS * TC_ROWS; }
+static inline int tc_pad(int n) { return (n + 2 * TC_ROWS - 1) / (2 * TC_ROWS) * (2 * TC_ROWS); }   // a CTA pair = 512 rows
 
 void carve_mnn_tc(Bump& bump, int batch, int n1_max, int n2_max, MnnTcWs& ws) {
   const int n_pad = tc_pad(n1_max > n2_max ? n1_max : n2_max);
@@ -614,6 +813,17 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
   *best12 = ws.best12;
   *best21 = ws.best21;
   XF_CUDA(cudaMemsetAsync(ws.best21, 0, sizeof(unsigned long long) * (size_t)batch * n2_max, st));
+  if (once == 2) {   // CTA-pair kernel (cta_group::2)
+    static bool attr2 = false;
+    if (!attr2) {
+      XF_CUDA(cudaFuncSetAttribute(mnn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
+      attr2 = true;
+    }
+    dim3 grid2(n_pad / TC_ROWS, batch, 2);   // even by construction (n_pad is a multiple of 512): clusters of 2 along x
+    mnn_tc2_kernel<<<grid2, TC_THREADS, TC2_SMEM, st>>>(maps, n1, n1_max, n2, n2_max, n_pad, ws.best12, ws.best21);
+    XF_LAUNCH_CHECK();
+    return XF_OK;
+  }
   if (once) {
     dim3 grid1(n_pad / TC_ROWS, batch);
     mnn_tc_once_kernel<<<grid1, TC1_THREADS, TC1_SMEM, st>>>(maps, n1, n1_max, n2, n2_max, n_pad, ws.best12, ws.best21);

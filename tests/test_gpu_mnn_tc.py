@@ -55,7 +55,7 @@ def run(xf, f1, f2, thr):
     return i0.cpu().numpy(), i1.cpu().numpy()
 
 
-TC_IMPLS = [1, 2]   # 1: one GEMM per direction, 2: single pass (row arg-max + column maxima from one accumulator tile)
+TC_IMPLS = [1, 2, 3]   # 1: one GEMM per direction, 2: single pass (row + column arg-max from one accumulator tile), 3: 1 on CTA pairs
 
 
 @pytest.mark.parametrize("impl", TC_IMPLS)
@@ -134,7 +134,7 @@ def test_tc_full_size_identity(xf, impl):
     assert torch.equal(idx0, idx1) and torch.equal(idx0[3], torch.arange(4096, device="cuda"))
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 def test_exact_ties_first_index(xf, impl):
     """Duplicate descriptors give bit-equal similarities: torch's first-index rule decides (xfeat.py:333-339).  Rows 3/700
     of set 1 and rows 10/450 of set 2 are duplicated; values are small integers / 8 so every product and sum is exact in
