@@ -67,54 +67,59 @@ __global__ void __launch_bounds__(256) gray_resize_kernel(const void* __restrict
 
 // Fast path of gray_resize_kernel for the common case (BASELINE configs): fp32 input already at network resolution
 // (the bilinear resize is the identity: src == dst, lambda == 0), unit pixel stride, 16-byte aligned rows.
-// 4 pixels per thread, 128-bit loads per channel; same arithmetic as the generic kernel restricted to that case.
+// The image is walked as a linear array of 4-pixel groups (a 2-D block tiling left 7/8 of every second block idle at W = 640),
+// 4 groups per thread, and the loads of up to 4 channels x 4 groups are all issued before the first use; same per-pixel
+// arithmetic as the generic kernel restricted to that case.
+constexpr int GI_NPT = 4;
 __global__ void __launch_bounds__(256) gray_identity_f32_kernel(const float* __restrict__ img, int C, int64_t sb, int64_t sc,
                                                                 int64_t sh, int div255, int H, int W4,
                                                                 float* __restrict__ gray, double* __restrict__ stats) {
-  // each thread: two groups of 4 pixels (x4 and x4 + 64*gridDim.x-stride within the row tile), 2*C 128-bit loads in flight
   const int b = blockIdx.z;
-  const int xa = blockIdx.x * 128 + (threadIdx.x & 63), xb = xa + 64;
-  const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
-  const bool ina = (xa < W4) && (y < H), inb = (xb < W4) && (y < H);
-  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
-  if (ina) {
-    const float* p = img + (int64_t)b * sb + (int64_t)y * sh;
-    // channels in groups of 4 with every load of a group issued before the first use (a runtime-length loop of dependent
-    // load -> add pairs kept only two loads in flight per thread: 3.4 TB/s)
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c0 = 0; c0 < C; c0 += 4) {
-      float4 la[4], lb[4];
+  const unsigned n4 = (unsigned)H * (unsigned)W4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned e[GI_NPT];
+  bool in[GI_NPT];
+  const float* p[GI_NPT];
+  float4 g[GI_NPT];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool cin = c0 + u < C;
-        la[u] = cin ? __ldg(reinterpret_cast<const float4*>(p + (int64_t)(c0 + u) * sc + 4 * xa)) : zero4;
-        lb[u] = (cin && inb) ? __ldg(reinterpret_cast<const float4*>(p + (int64_t)(c0 + u) * sc + 4 * xb)) : zero4;
-      }
+  for (int k = 0; k < GI_NPT; ++k) {
+    e[k] = ((unsigned)blockIdx.x * GI_NPT + k) * 256u + threadIdx.x;
+    in[k] = e[k] < n4;
+    const unsigned y = in[k] ? e[k] / (unsigned)W4 : 0u, x4 = in[k] ? e[k] - y * (unsigned)W4 : 0u;
+    p[k] = img + (int64_t)b * sb + (int64_t)y * sh + 4 * x4;
+    g[k] = zero4;
+  }
+  for (int c0 = 0; c0 < C; c0 += 4) {
+    float4 l[4][GI_NPT];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (c0 + u < C) {
-          float4 va = la[u], vb = lb[u];
-          if (div255) {
-            va.x = __fdiv_rn(va.x, 255.f); va.y = __fdiv_rn(va.y, 255.f); va.z = __fdiv_rn(va.z, 255.f); va.w = __fdiv_rn(va.w, 255.f);
-            vb.x = __fdiv_rn(vb.x, 255.f); vb.y = __fdiv_rn(vb.y, 255.f); vb.z = __fdiv_rn(vb.z, 255.f); vb.w = __fdiv_rn(vb.w, 255.f);
-          }
-          ga.x = __fadd_rn(ga.x, va.x); ga.y = __fadd_rn(ga.y, va.y); ga.z = __fadd_rn(ga.z, va.z); ga.w = __fadd_rn(ga.w, va.w);
-          gb.x = __fadd_rn(gb.x, vb.x); gb.y = __fadd_rn(gb.y, vb.y); gb.z = __fadd_rn(gb.z, vb.z); gb.w = __fadd_rn(gb.w, vb.w);
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < GI_NPT; ++k)
+        l[u][k] = (c0 + u < C && in[k]) ? __ldg(reinterpret_cast<const float4*>(p[k] + (int64_t)(c0 + u) * sc)) : zero4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c0 + u < C) {
+#pragma unroll
+        for (int k = 0; k < GI_NPT; ++k) {
+          float4 v = l[u][k];
+          if (div255) { v.x = __fdiv_rn(v.x, 255.f); v.y = __fdiv_rn(v.y, 255.f); v.z = __fdiv_rn(v.z, 255.f); v.w = __fdiv_rn(v.w, 255.f); }
+          g[k].x = __fadd_rn(g[k].x, v.x); g[k].y = __fadd_rn(g[k].y, v.y); g[k].z = __fadd_rn(g[k].z, v.z); g[k].w = __fadd_rn(g[k].w, v.w);
         }
       }
     }
+  }
+  double s = 0.0, ss = 0.0;
+  float4* out = reinterpret_cast<float4*>(gray + (int64_t)b * H * W4 * 4);
+#pragma unroll
+  for (int k = 0; k < GI_NPT; ++k) {
     if (C != 1) {
       const float fc = (float)C;
-      ga.x = __fdiv_rn(ga.x, fc); ga.y = __fdiv_rn(ga.y, fc); ga.z = __fdiv_rn(ga.z, fc); ga.w = __fdiv_rn(ga.w, fc);
-      gb.x = __fdiv_rn(gb.x, fc); gb.y = __fdiv_rn(gb.y, fc); gb.z = __fdiv_rn(gb.z, fc); gb.w = __fdiv_rn(gb.w, fc);
+      g[k].x = __fdiv_rn(g[k].x, fc); g[k].y = __fdiv_rn(g[k].y, fc); g[k].z = __fdiv_rn(g[k].z, fc); g[k].w = __fdiv_rn(g[k].w, fc);
     }
-    float4* row = reinterpret_cast<float4*>(gray + ((int64_t)b * H + y) * (W4 * 4));
-    row[xa] = ga;
-    if (inb) row[xb] = gb;
+    if (in[k]) out[e[k]] = g[k];     // out-of-range groups hold zeros and add nothing to the sums
+    s += ((double)g[k].x + (double)g[k].y) + ((double)g[k].z + (double)g[k].w);
+    ss += (double)g[k].x * g[k].x + (double)g[k].y * g[k].y + (double)g[k].z * g[k].z + (double)g[k].w * g[k].w;
   }
-  double s = ((double)ga.x + (double)ga.y) + ((double)ga.z + (double)ga.w) + ((double)gb.x + (double)gb.y) + ((double)gb.z + (double)gb.w);
-  double ss = (double)ga.x * ga.x + (double)ga.y * ga.y + (double)ga.z * ga.z + (double)ga.w * ga.w +
-              (double)gb.x * gb.x + (double)gb.y * gb.y + (double)gb.z * gb.z + (double)gb.w * gb.w;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -268,7 +273,7 @@ extern "C" int xfeat_preprocess(const void* d_img, int dtype, int B, int C, int 
     xf::gray_identity_u8hwc_kernel<<<g4, 256, 0, st>>>((const unsigned char*)d_img, stride_b, stride_h, div255, H, W / 4, d_xn,
                                                        d_stats);
   } else if (fast) {
-    dim3 g4(xf::cdiv(W / 4, 128), xf::cdiv(H, 4), B);
+    dim3 g4(xf::cdiv(H * (W / 4), 256 * xf::GI_NPT), 1, B);
     xf::gray_identity_f32_kernel<<<g4, 256, 0, st>>>((const float*)d_img, C, stride_b, stride_c, stride_h, div255, H, W / 4,
                                                      d_xn, d_stats);
   } else if (dtype == XF_DTYPE_F32)

@@ -348,6 +348,27 @@ __device__ __forceinline__ float4 bicubic4(const float* __restrict__ fb, const f
   const float cx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2((1.f - tx) + 1.f)};
   const float cy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2((1.f - ty) + 1.f)};
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x0 >= 0 && x0 + 3 < Wm && y0 >= 0 && y0 + 3 < Hm) {
+    // interior keypoint (almost all): no per-tap bounds tests, 32-bit offsets from one base pointer -- the same loads and
+    // the same arithmetic in the same order as the general path below (the kernel is issue-bound: ncu 75 % issue-active)
+    const float4* p0 = reinterpret_cast<const float4*>(fb) + (uint32_t)(y0 * Wm + x0) * 16u + (uint32_t)l16;
+    const float* d0 = db + (uint32_t)(y0 * Wm + x0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 v = __ldg(p0 + (uint32_t)(i * Wm + j) * 16u);
+        const float d = __ldg(d0 + (uint32_t)(i * Wm + j));
+        v.x *= d; v.y *= d; v.z *= d; v.w *= d;
+        rr.x = fmaf(v.x, cx[j], rr.x); rr.y = fmaf(v.y, cx[j], rr.y);
+        rr.z = fmaf(v.z, cx[j], rr.z); rr.w = fmaf(v.w, cx[j], rr.w);
+      }
+      o.x = fmaf(rr.x, cy[i], o.x); o.y = fmaf(rr.y, cy[i], o.y);
+      o.z = fmaf(rr.z, cy[i], o.z); o.w = fmaf(rr.w, cy[i], o.w);
+    }
+    return o;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int yy = y0 + i;
