@@ -33,6 +33,7 @@ SIGNATURES = {
     "xfeat_get_mnn_impl": (c_i, []),
     "xfeat_mnn_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
     "xfeat_mnn_match": (c_i, [c_p, c_p, c_i, c_i64, c_p, c_p, c_i, c_i64, c_i, c_f, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "xfeat_mnn_match_bounded": (c_i, [c_p, c_p, c_i, c_i64, c_p, c_p, c_i, c_i64, c_i, c_f, c_f, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "xfeat_gather_matches": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p]),
     "xfeat_refine_workspace_bytes": (c_sz, [c_i, c_i]),
     "xfeat_refine": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_sz, c_p]),

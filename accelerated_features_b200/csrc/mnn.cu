@@ -206,7 +206,7 @@ static void carve_mnn(Bump& bump, int batch, int n1_max, int n2_max, MnnWs& ws) 
 size_t mnn_tc_workspace_bytes(int batch, int n1_max, int n2_max);
 int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, const float* f2, const int* n2, int n2_max,
                   int64_t stride2, int batch, void* d_ws, size_t ws_bytes, unsigned long long** best12,
-                  unsigned long long** best21, float** inv_s2, cudaStream_t st, int once);
+                  unsigned long long** best21, float** inv_s2, cudaStream_t st, int once, float abs_bound);
 // 0 = fp32 CUDA cores, 1 = tcgen05 split-fp16 with one GEMM per direction (default), 2 = tcgen05 single pass: one GEMM, the
 // column arg-max by cross-lane reduction in the epilogue -- same results, but the epilogue then out-weighs the saved GEMM
 // (64 x 4096 x 4096: 0.75 ms vs 0.68 ms per call, tools/mnn_ab.py), so it is kept selectable, not default;
@@ -230,6 +230,14 @@ extern "C" int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_ma
                                const int32_t* d_n2, int n2_max, int64_t stride2, int batch, float min_cossim,
                                int64_t* d_idx0, int64_t* d_idx1, int32_t* d_n_matches, void* d_ws, size_t ws_bytes,
                                void* stream) {
+  return xfeat_mnn_match_bounded(d_f1, d_n1, n1_max, stride1, d_f2, d_n2, n2_max, stride2, batch, min_cossim, 0.f, d_idx0, d_idx1,
+                                 d_n_matches, d_ws, ws_bytes, stream);
+}
+
+extern "C" int xfeat_mnn_match_bounded(const float* d_f1, const int32_t* d_n1, int n1_max, int64_t stride1, const float* d_f2,
+                                       const int32_t* d_n2, int n2_max, int64_t stride2, int batch, float min_cossim,
+                                       float abs_bound, int64_t* d_idx0, int64_t* d_idx1, int32_t* d_n_matches, void* d_ws,
+                                       size_t ws_bytes, void* stream) {
   XF_REQUIRE(d_f1 && d_f2 && d_idx0 && d_idx1 && d_n_matches && d_ws, "mnn_match: null pointer");
   XF_REQUIRE(batch > 0 && batch <= 65535 && n1_max > 0 && n2_max > 0, "mnn_match: bad sizes");
   XF_REQUIRE(((uintptr_t)d_f1 % 16) == 0 && ((uintptr_t)d_f2 % 16) == 0 && stride1 % 4 == 0 && stride2 % 4 == 0,
@@ -239,7 +247,7 @@ extern "C" int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_ma
     unsigned long long *b12 = nullptr, *b21 = nullptr;
     float* inv_s2 = nullptr;
     int rc = xf::launch_mnn_tc(d_f1, d_n1, n1_max, stride1, d_f2, d_n2, n2_max, stride2, batch, d_ws, ws_bytes, &b12, &b21,
-                               &inv_s2, st, xf::g_mnn_impl == 2 ? 1 : (xf::g_mnn_impl == 3 ? 2 : 0));
+                               &inv_s2, st, xf::g_mnn_impl == 2 ? 1 : (xf::g_mnn_impl == 3 ? 2 : 0), abs_bound);
     if (rc) return rc;
     xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(b12, b21, d_n1, n1_max, n2_max, min_cossim, inv_s2, (long long*)d_idx0,
                                                     (long long*)d_idx1, d_n_matches);

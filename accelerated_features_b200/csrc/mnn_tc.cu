@@ -1,15 +1,17 @@
 // Mutual-NN similarity scan on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-equivalent precision.
 //
 // fp32-equivalent via operand splitting: x*s = hi + lo with hi, lo in fp16 (s = power of two chosen from max|x| so that
-// hi uses the fp16 range and lo stays normal), and one K = 192 fp16 GEMM with fp32 accumulation
-//      F1' = [hi1 | hi1 | lo1]   F2' = [hi2 | lo2 | hi2]   =>   F1' F2'^T = hi1.hi2 + hi1.lo2 + lo1.hi2
-// (the dropped lo.lo term is ~2^-22 relative, below fp32 accumulation noise).  The same two arrays serve both scan
-// directions (rows of F1 against F2, rows of F2 against F1): the three K-blocks pair the same factors in the same order,
-// so S12[i][j] and S21[j][i] are bit-identical.
+// hi uses the fp16 range and lo stays normal), rows stored as [hi(64) | lo(64)] halves, and three K = 64 fp16 GEMM blocks
+// with fp32 accumulation into the same TMEM tile
+//      S = hi1.hi2^T + hi1.lo2^T + lo1.hi2^T
+// (the dropped lo.lo term is ~2^-22 relative, below fp32 accumulation noise).  The blocks are selected by the UMMA
+// descriptor addresses (hi box / lo box of each operand), so nothing is stored twice.  The same two arrays serve both scan
+// directions (rows of F1 against F2, rows of F2 against F1), which add the same three products in the same order:
+// S12[i][j] and S21[j][i] are bit-identical.
 //
 // One CTA = 256 rows (two M=128 accumulator slabs) x all 128-column tiles of the other set:
 //   warp 0   : TMA producer (A slabs once, then the B tile ring, 128B-swizzled K-major boxes of 64 halves x 128 rows)
-//   warp 1   : TMEM allocation + single-thread tcgen05.mma issue (2 slabs x 12 UMMA 128x128x16 per tile)
+//   warp 1   : TMEM allocation + single-thread tcgen05.mma issue (2 slabs x 3 K-blocks x 4 UMMA 128x128x16 per tile)
 //   warps 2-5: epilogue, one TMEM lane quarter each: tcgen05.ld 32 columns at a time, running row arg-max in registers
 // The accumulators are double buffered in TMEM (2 x 256 columns), so the arg-max of tile t overlaps the MMAs of t+1.
 // Nothing but the final (value, index) per row ever leaves the SM.
@@ -32,11 +34,11 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-constexpr int TC_ROWS = 256, TC_BN = 128, TC_KP = 192, TC_BOX_BYTES = 128 * 128;  // 128 rows x 128 B
+constexpr int TC_ROWS = 256, TC_BN = 128, TC_KP = 128, TC_BOX_BYTES = 128 * 128;  // operand row [hi(64) | lo(64)]; box = 128 rows x 128 B
 constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
-constexpr size_t TC_SMEM = 1024 + 12 * (size_t)TC_BOX_BYTES + 256 + 2 * 128 * 8;
+constexpr size_t TC_SMEM = 1024 + 8 * (size_t)TC_BOX_BYTES + 256 + 2 * 128 * 8;
 constexpr int TC1_EPI_WARPS = 16, TC1_THREADS = 64 + 32 * TC1_EPI_WARPS;   // single-pass variant: warps 2-17 epilogue
-constexpr size_t TC1_SMEM = 1024 + 12 * (size_t)TC_BOX_BYTES + 256 + 3 * 2 * 128 * 8 + 2 * 2 * 4 * 128 * 4 + TC1_EPI_WARPS * 64 * 4;
+constexpr size_t TC1_SMEM = 1024 + 8 * (size_t)TC_BOX_BYTES + 256 + 3 * 2 * 128 * 8 + 2 * 2 * 4 * 128 * 4 + TC1_EPI_WARPS * 64 * 4;
 
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ f, const int* __restrict__ np, int n_max,
                                                      int64_t stride, unsigned* __restrict__ out) {
@@ -53,16 +55,16 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ f
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
-// One warp per row: writes the 192-half split row (second_is_lo = 0: [hi|hi|lo], 1: [hi|lo|hi]); zero rows past n.
+// One warp per row: writes the 128-half split row [hi(64) | lo(64)]; zero rows past n.
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ f, const int* __restrict__ np, int n_max,
                                                     int n_pad, int64_t stride, const unsigned* __restrict__ absmax,
-                                                    int b_type, __half* __restrict__ out, float* __restrict__ inv_s2) {
+                                                    float abs_bound, __half* __restrict__ out, float* __restrict__ inv_s2) {
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int pair = blockIdx.y;
   if (wid >= n_pad) return;
   const int n = np ? min(np[pair], n_max) : n_max;
-  const float mx = __uint_as_float(*absmax);
+  const float mx = abs_bound > 0.f ? abs_bound : __uint_as_float(*absmax);   // caller's bound or the measured maximum
   int e = 0;
   if (mx > 0.f) frexpf(mx, &e);                 // mx = m * 2^e, m in [0.5, 1)  ->  mx < 2^e
   const float s = (mx > 0.f) ? ldexpf(1.f, 14 - e) : 1.f;   // mx * s in [2^13, 2^14)
@@ -77,8 +79,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ f,
   }
   __half2* o = reinterpret_cast<__half2*>(out + ((int64_t)pair * n_pad + wid) * TC_KP);
   o[lane] = hi;
-  o[32 + lane] = b_type ? lo : hi;
-  o[64 + lane] = b_type ? hi : lo;
+  o[32 + lane] = lo;
 }
 
 struct TcMaps {
@@ -103,9 +104,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = base;                       // [slab 2][kb 3] boxes
-  unsigned char* sB = base + 6 * TC_BOX_BYTES;    // [stage 2][kb 3] boxes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 12 * TC_BOX_BYTES);
+  unsigned char* sA = base;                       // [slab 2][hi, lo] boxes
+  unsigned char* sB = base + 4 * TC_BOX_BYTES;    // [stage 2][hi, lo] boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 8 * TC_BOX_BYTES);
   uint64_t* a_full = bars;
   uint64_t* b_full = bars + 1;     // [2]
   uint64_t* b_empty = bars + 3;    // [2]
@@ -142,17 +143,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
     if (tc::elect_one()) {
       // ---------------- TMA producer ----------------
       const int arow = pair * n_pad + row0;
-      tc::mbar_expect_tx(a_full, 6 * TC_BOX_BYTES);
+      tc::mbar_expect_tx(a_full, 4 * TC_BOX_BYTES);
       for (int slab = 0; slab < 2; ++slab)
-        for (int kb = 0; kb < 3; ++kb)
-          tc::tma_load_2d(sA + (slab * 3 + kb) * TC_BOX_BYTES, mapA, a_full, kb * 64, arow + slab * 128);
+        for (int kb = 0; kb < 2; ++kb)
+          tc::tma_load_2d(sA + (slab * 2 + kb) * TC_BOX_BYTES, mapA, a_full, kb * 64, arow + slab * 128);
       const int brow = pair * n_pad;
       for (int t = 0; t < T; ++t) {
         const int s = t & 1;
         tc::mbar_wait(&b_empty[s], ((t >> 1) & 1) ^ 1);
-        tc::mbar_expect_tx(&b_full[s], 3 * TC_BOX_BYTES);
-        for (int kb = 0; kb < 3; ++kb)
-          tc::tma_load_2d(sB + (s * 3 + kb) * TC_BOX_BYTES, mapB, &b_full[s], kb * 64, brow + t * TC_BN);
+        tc::mbar_expect_tx(&b_full[s], 2 * TC_BOX_BYTES);
+        for (int kb = 0; kb < 2; ++kb)
+          tc::tma_load_2d(sB + (s * 2 + kb) * TC_BOX_BYTES, mapB, &b_full[s], kb * 64, brow + t * TC_BN);
       }
     }
     __syncwarp();
@@ -160,6 +161,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
     if (tc::elect_one()) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, TC_BN);
+      // K-blocks of x.y = hi.hi + hi.lo + lo.hi, taken from the [hi | lo] boxes of the two operands.  Direction 1 (A = F2,
+      // B = F1) swaps the roles of the last two blocks so both directions add the same three products in the same order and
+      // S12[i][j] == S21[j][i] bit for bit.
+      const int a_sel[3] = {0, dir ? 1 : 0, dir ? 0 : 1};
+      const int b_sel[3] = {0, dir ? 0 : 1, dir ? 1 : 0};
       tc::mbar_wait(a_full, 0);
       for (int t = 0; t < T; ++t) {
         const int s = t & 1, ph = (t >> 1) & 1;
@@ -171,8 +177,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
           const uint32_t d = tmem + s * 256 + slab * 128;
 #pragma unroll
           for (int kb = 0; kb < 3; ++kb) {
-            const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + (slab * 3 + kb) * TC_BOX_BYTES), 1024);
-            const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 3 + kb) * TC_BOX_BYTES), 1024);
+            const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + (slab * 2 + a_sel[kb]) * TC_BOX_BYTES), 1024);
+            const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 2 + b_sel[kb]) * TC_BOX_BYTES), 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // 16 halves = 32 B = 2 x 16-byte units along K inside the 128 B swizzle row
               tc::umma_f16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
@@ -305,9 +311,9 @@ __global__ void __launch_bounds__(TC1_THREADS, 1) mnn_tc_once_kernel(const __gri
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = base;                       // [slab 2][kb 3] boxes
-  unsigned char* sB = base + 6 * TC_BOX_BYTES;    // [stage 2][kb 3] boxes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 12 * TC_BOX_BYTES);
+  unsigned char* sA = base;                       // [slab 2][hi, lo] boxes
+  unsigned char* sB = base + 4 * TC_BOX_BYTES;    // [stage 2][hi, lo] boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 8 * TC_BOX_BYTES);
   uint64_t* a_full = bars;
   uint64_t* b_full = bars + 1;     // [2]
   uint64_t* b_empty = bars + 3;    // [2]
@@ -347,17 +353,17 @@ __global__ void __launch_bounds__(TC1_THREADS, 1) mnn_tc_once_kernel(const __gri
     if (tc::elect_one()) {
       // ---------------- TMA producer ----------------
       const int arow = pair * n_pad + row0;
-      tc::mbar_expect_tx(a_full, 6 * TC_BOX_BYTES);
+      tc::mbar_expect_tx(a_full, 4 * TC_BOX_BYTES);
       for (int slab = 0; slab < 2; ++slab)
-        for (int kb = 0; kb < 3; ++kb)
-          tc::tma_load_2d(sA + (slab * 3 + kb) * TC_BOX_BYTES, &maps.m1, a_full, kb * 64, arow + slab * 128);
+        for (int kb = 0; kb < 2; ++kb)
+          tc::tma_load_2d(sA + (slab * 2 + kb) * TC_BOX_BYTES, &maps.m1, a_full, kb * 64, arow + slab * 128);
       const int brow = pair * n_pad;
       for (int t = 0; t < T; ++t) {
         const int s = t & 1;
         tc::mbar_wait(&b_empty[s], ((t >> 1) & 1) ^ 1);
-        tc::mbar_expect_tx(&b_full[s], 3 * TC_BOX_BYTES);
-        for (int kb = 0; kb < 3; ++kb)
-          tc::tma_load_2d(sB + (s * 3 + kb) * TC_BOX_BYTES, &maps.m2, &b_full[s], kb * 64, brow + t * TC_BN);
+        tc::mbar_expect_tx(&b_full[s], 2 * TC_BOX_BYTES);
+        for (int kb = 0; kb < 2; ++kb)
+          tc::tma_load_2d(sB + (s * 2 + kb) * TC_BOX_BYTES, &maps.m2, &b_full[s], kb * 64, brow + t * TC_BN);
       }
     }
     __syncwarp();
@@ -365,6 +371,9 @@ __global__ void __launch_bounds__(TC1_THREADS, 1) mnn_tc_once_kernel(const __gri
     if (tc::elect_one()) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, TC_BN);
+      // K-blocks of x.y = hi.hi + hi.lo + lo.hi, taken from the [hi | lo] boxes of the two operands
+      constexpr int a_sel[3] = {0, 0, 1};
+      constexpr int b_sel[3] = {0, 1, 0};
       tc::mbar_wait(a_full, 0);
       for (int t = 0; t < T; ++t) {
         const int s = t & 1, ph = (t >> 1) & 1;
@@ -376,8 +385,8 @@ __global__ void __launch_bounds__(TC1_THREADS, 1) mnn_tc_once_kernel(const __gri
           const uint32_t d = tmem + s * 256 + slab * 128;
 #pragma unroll
           for (int kb = 0; kb < 3; ++kb) {
-            const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + (slab * 3 + kb) * TC_BOX_BYTES), 1024);
-            const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 3 + kb) * TC_BOX_BYTES), 1024);
+            const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + (slab * 2 + a_sel[kb]) * TC_BOX_BYTES), 1024);
+            const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 2 + b_sel[kb]) * TC_BOX_BYTES), 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               tc::umma_f16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
@@ -544,7 +553,7 @@ __global__ void __launch_bounds__(TC1_THREADS, 1) mnn_tc_once_kernel(const __gri
 // accumulator-full barriers are per CTA and are signalled by multicast tcgen05.commit; accumulator-empty lives in the leader
 // and counts the epilogue warps of both CTAs (remote mbarrier.arrive through mapa).
 constexpr int TC2_BN = 256;
-constexpr size_t TC2_SMEM = 1024 + 12 * (size_t)TC_BOX_BYTES + 256 + 2 * 128 * 8;
+constexpr size_t TC2_SMEM = 1024 + 8 * (size_t)TC_BOX_BYTES + 256 + 2 * 128 * 8;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     mnn_tc2_kernel(const __grid_constant__ TcMaps maps, const int* __restrict__ n1p, int n1_max, const int* __restrict__ n2p,
@@ -564,9 +573,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = base;                       // [slab 2][kb 3] 128-row boxes
-  unsigned char* sB = base + 6 * TC_BOX_BYTES;    // [stage 2][kb 3] 128-row boxes = this CTA's half of a 256-column tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 12 * TC_BOX_BYTES);
+  unsigned char* sA = base;                       // [slab 2][hi, lo] 128-row boxes
+  unsigned char* sB = base + 4 * TC_BOX_BYTES;    // [stage 2][hi, lo] 128-row boxes = this CTA's half of a 256-column tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + 8 * TC_BOX_BYTES);
   uint64_t* a_full = bars;         // leader: A slabs of both CTAs landed
   uint64_t* b_full = bars + 1;     // [2 stages] leader: both halves of the B stage landed
   uint64_t* b_empty = bars + 3;    // [2 stages] per CTA (multicast commit)
@@ -604,18 +613,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       // ---------------- TMA producer (both CTAs; bytes are reported to the leader's barriers) ----------------
       const uint32_t a_full_l = tc::mapa_rank(tc::smem_u32(a_full), 0);
       const int arow = pair * n_pad + row0;
-      if (leader) tc::mbar_expect_tx(a_full, 2 * 6 * TC_BOX_BYTES);
+      if (leader) tc::mbar_expect_tx(a_full, 2 * 4 * TC_BOX_BYTES);
       for (int slab = 0; slab < 2; ++slab)
-        for (int kb = 0; kb < 3; ++kb)
-          tc::tma_load_2d_2sm(sA + (slab * 3 + kb) * TC_BOX_BYTES, mapA, a_full_l, kb * 64, arow + slab * 128);
+        for (int kb = 0; kb < 2; ++kb)
+          tc::tma_load_2d_2sm(sA + (slab * 2 + kb) * TC_BOX_BYTES, mapA, a_full_l, kb * 64, arow + slab * 128);
       const int brow = pair * n_pad + (int)rank * 128;   // this CTA's half of every 256-row B tile
       for (int t = 0; t < T; ++t) {
         const int s = t & 1;
         tc::mbar_wait(&b_empty[s], ((t >> 1) & 1) ^ 1);
-        if (leader) tc::mbar_expect_tx(&b_full[s], 2 * 3 * TC_BOX_BYTES);
+        if (leader) tc::mbar_expect_tx(&b_full[s], 2 * 2 * TC_BOX_BYTES);
         const uint32_t b_full_l = tc::mapa_rank(tc::smem_u32(&b_full[s]), 0);
-        for (int kb = 0; kb < 3; ++kb)
-          tc::tma_load_2d_2sm(sB + (s * 3 + kb) * TC_BOX_BYTES, mapB, b_full_l, kb * 64, brow + t * TC2_BN);
+        for (int kb = 0; kb < 2; ++kb)
+          tc::tma_load_2d_2sm(sB + (s * 2 + kb) * TC_BOX_BYTES, mapB, b_full_l, kb * 64, brow + t * TC2_BN);
       }
     }
     __syncwarp();
@@ -623,6 +632,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     if (leader && tc::elect_one()) {
       // ---------------- MMA issuer (leader only): M = 256 across the pair, N = 256 ----------------
       constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 256, TC2_BN);
+      // K-blocks of x.y = hi.hi + hi.lo + lo.hi, taken from the [hi | lo] boxes of the two operands.  Direction 1 (A = F2,
+      // B = F1) swaps the roles of the last two blocks so both directions add the same three products in the same order and
+      // S12[i][j] == S21[j][i] bit for bit.
+      const int a_sel[3] = {0, dir ? 1 : 0, dir ? 0 : 1};
+      const int b_sel[3] = {0, dir ? 0 : 1, dir ? 1 : 0};
       tc::mbar_wait_cluster(a_full, 0);
       for (int t = 0; t < T; ++t) {
         const int s = t & 1;
@@ -634,8 +648,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           const uint32_t d = tmem + slab * TC2_BN;
 #pragma unroll
           for (int kb = 0; kb < 3; ++kb) {
-            const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + (slab * 3 + kb) * TC_BOX_BYTES), 1024);
-            const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 3 + kb) * TC_BOX_BYTES), 1024);
+            const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + (slab * 2 + a_sel[kb]) * TC_BOX_BYTES), 1024);
+            const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 2 + b_sel[kb]) * TC_BOX_BYTES), 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc::umma_f16_2sm(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
           }
@@ -778,7 +792,7 @@ static int make_map(CUtensorMap* m, const __half* ptr, uint64_t rows) {
 // Fills best12 (rows of F1 -> arg-max column in F2) and best21 (rows of F2 -> arg-max in F1), packed (value*s^2, index).
 int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, const float* f2, const int* n2, int n2_max,
                   int64_t stride2, int batch, void* d_ws, size_t ws_bytes, unsigned long long** best12,
-                  unsigned long long** best21, float** inv_s2, cudaStream_t st, int once) {
+                  unsigned long long** best21, float** inv_s2, cudaStream_t st, int once, float abs_bound) {
   Bump bump(d_ws, ws_bytes);
   MnnTcWs ws;
   carve_mnn_tc(bump, batch, n1_max, n2_max, ws);
@@ -788,15 +802,17 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
   }
   const int n_pad = tc_pad(n1_max > n2_max ? n1_max : n2_max);
   XF_REQUIRE((int64_t)batch * n_pad < (1ll << 31), "mnn_match(tcgen05): batch * n too large");
-  XF_CUDA(cudaMemsetAsync(ws.absmax, 0, sizeof(unsigned), st));
-  absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(f1, n1, n1_max, stride1, ws.absmax);
-  XF_LAUNCH_CHECK();
-  absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(f2, n2, n2_max, stride2, ws.absmax);
-  XF_LAUNCH_CHECK();
+  if (!(abs_bound > 0.f)) {   // no bound from the caller: max |x| over both sets fixes the power-of-two operand scale
+    XF_CUDA(cudaMemsetAsync(ws.absmax, 0, sizeof(unsigned), st));
+    absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(f1, n1, n1_max, stride1, ws.absmax);
+    XF_LAUNCH_CHECK();
+    absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(f2, n2, n2_max, stride2, ws.absmax);
+    XF_LAUNCH_CHECK();
+  }
   const dim3 sgrid(cdiv(n_pad * 32, 256), batch);
-  split_kernel<<<sgrid, 256, 0, st>>>(f1, n1, n1_max, n_pad, stride1, ws.absmax, 0, ws.f1s, ws.inv_s2);
+  split_kernel<<<sgrid, 256, 0, st>>>(f1, n1, n1_max, n_pad, stride1, ws.absmax, abs_bound, ws.f1s, ws.inv_s2);
   XF_LAUNCH_CHECK();
-  split_kernel<<<sgrid, 256, 0, st>>>(f2, n2, n2_max, n_pad, stride2, ws.absmax, 1, ws.f2s, nullptr);
+  split_kernel<<<sgrid, 256, 0, st>>>(f2, n2, n2_max, n_pad, stride2, ws.absmax, abs_bound, ws.f2s, nullptr);
   XF_LAUNCH_CHECK();
   TcMaps maps;
   int rc;

@@ -204,16 +204,19 @@ class XFeat:
         return [{"keypoints": out["keypoints"][b, :n[b]], "scores": out["scores"][b, :n[b]],
                  "descriptors": out["descriptors"][b, :n[b]]} for b in range(len(n))]
 
-    def _mnn_device(self, f1, n1, n1_max, stride1, f2, n2, n2_max, stride2, batch, min_cossim):
+    def _mnn_device(self, f1, n1, n1_max, stride1, f2, n2, n2_max, stride2, batch, min_cossim, abs_bound=0.0):
+        """abs_bound > 0: the caller guarantees max|f| <= abs_bound (1.0 for the sparse path's unit-norm descriptors), which
+        spares the tensor-core matcher its max-reduction pass over both descriptor sets."""
         idx0 = self._empty((batch, n1_max), torch.int64)
         idx1 = self._empty((batch, n1_max), torch.int64)
         cnt = self._empty((batch,), torch.int32)
         ws = self._workspace(self._lib.xfeat_mnn_workspace_bytes(batch, n1_max, n2_max))
         with torch.cuda.device(self.dev):
-            _lib.check(self._lib.xfeat_mnn_match(f1.data_ptr(), _ptr(n1), n1_max, stride1, f2.data_ptr(), _ptr(n2), n2_max,
-                                                 stride2, batch, float(min_cossim), idx0.data_ptr(), idx1.data_ptr(),
-                                                 cnt.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()),
-                       "xfeat_mnn_match")
+            _lib.check(self._lib.xfeat_mnn_match_bounded(f1.data_ptr(), _ptr(n1), n1_max, stride1, f2.data_ptr(), _ptr(n2),
+                                                         n2_max, stride2, batch, float(min_cossim), float(abs_bound),
+                                                         idx0.data_ptr(), idx1.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
+                                                         ws.numel(), self._stream()),
+                       "xfeat_mnn_match_bounded")
         return idx0, idx1, cnt
 
     @staticmethod
@@ -261,7 +264,8 @@ class XFeat:
             o2 = self._detect_sparse_device(x2, top_k, self.detection_threshold, div255)
             k1, k2, d1, d2, n1, n2 = (o1["keypoints"], o2["keypoints"], o1["descriptors"], o2["descriptors"],
                                       o1["n_valid"], o2["n_valid"])
-        idx0, idx1, cnt = self._mnn_device(d1, n1, top_k, top_k * 64, d2, n2, top_k, top_k * 64, B, min_cossim)
+        idx0, idx1, cnt = self._mnn_device(d1, n1, top_k, top_k * 64, d2, n2, top_k, top_k * 64, B, min_cossim,
+                                           abs_bound=1.0)   # xfeat_detect_sparse writes unit-norm rows
         mk0, mk1 = self._empty((B, top_k, 2)), self._empty((B, top_k, 2))
         with torch.cuda.device(self.dev):
             _lib.check(self._lib.xfeat_gather_matches(k1.data_ptr(), k2.data_ptr(), top_k, top_k, idx0.data_ptr(),

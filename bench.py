@@ -291,14 +291,17 @@ def run_gpu(args):
         achieved = flops / (mnn_ms / 1e3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         tc = lib.xfeat_get_mnn_impl() >= 1
-        kname = ("mnn_tc_once_kernel (tcgen05 split-fp16 K=192 D1.D2^T, fp32 accumulate in TMEM, fused row + column arg-max; "
-                 "timed call also contains absmax/split/finalize)") if tc else "mnn_scan_kernel (fp32 FFMA D1.D2^T + fused row/col arg-max)"
+        impl = lib.xfeat_get_mnn_impl()
+        kname = {1: "mnn_tc_kernel (tcgen05 split-fp16, 3 K=64 blocks D1.D2^T, fp32 accumulate in TMEM, fused row arg-max, both directions",
+                 2: "mnn_tc_once_kernel (tcgen05 split-fp16, one GEMM, row + column arg-max in the epilogue",
+                 3: "mnn_tc2_kernel (tcgen05 cta_group::2 CTA pairs, split-fp16, fused row arg-max, both directions"}.get(
+            impl, "mnn_scan_kernel (fp32 FFMA D1.D2^T + fused row/col arg-max") + "; timed call also contains split/finalize)"
         ncu = None
         for name in ("ncu_mnn_tc_once.json", "ncu_mnn_tc_final.json"):
             try:
                 with open(os.path.join(ROOT, "profiles", "r01", name)) as f:
                     ncu = json.load(f)
-                if (ncu.get("kernel") == "mnn_tc_once_kernel") == (lib.xfeat_get_mnn_impl() == 2):
+                if (ncu.get("kernel") == "mnn_tc_once_kernel") == (impl == 2):
                     break
                 ncu = None
             except Exception:

@@ -136,6 +136,14 @@ XF_API int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_max, i
                     const float* d_f2, const int32_t* d_n2, int n2_max, int64_t stride2,
                     int batch, float min_cossim, int64_t* d_idx0, int64_t* d_idx1, int32_t* d_n_matches,
                     void* d_ws, size_t ws_bytes, void* stream);
+/* xfeat_mnn_match with a caller-supplied bound: abs_bound > 0 promises max |d_f1|, max |d_f2| <= abs_bound (1.0 for the
+ * unit-norm descriptors xfeat_detect_sparse writes), so the tensor-core implementations take their power-of-two operand
+ * scale from it instead of running a max-reduction over both descriptor sets first.  abs_bound <= 0: identical to
+ * xfeat_mnn_match.  The bound only selects the scale; results do not depend on it beyond accumulation-noise ties. */
+XF_API int xfeat_mnn_match_bounded(const float* d_f1, const int32_t* d_n1, int n1_max, int64_t stride1,
+                            const float* d_f2, const int32_t* d_n2, int n2_max, int64_t stride2,
+                            int batch, float min_cossim, float abs_bound, int64_t* d_idx0, int64_t* d_idx1,
+                            int32_t* d_n_matches, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Gather matched keypoints: out0[b][m] = kpts0[b][idx0[b][m]], out1[b][m] = kpts1[b][idx1[b][m]] for m < n_matches[b]
  * (replaces the fancy-indexing at xfeat.py:186). kpts are (batch, n_max, 2) f32. */

@@ -151,3 +151,24 @@ def test_exact_ties_first_index(xf, impl):
         g0, g1 = run(xf, f1, f2, -1)
     assert np.array_equal(g0, w0.numpy()) and np.array_equal(g1, w1.numpy())
     assert 3 in g0 and 700 not in g0 and 701 not in g0
+
+
+@pytest.mark.parametrize("impl", TC_IMPLS)
+def test_bounded_scale_matches_measured_scale(xf, impl):
+    """xfeat_mnn_match_bounded(abs_bound=1) on unit-norm descriptors: same matches as the max-reduction path (the bound only
+    picks the power-of-two operand scale), and the same as the oracle modulo accumulation-noise ties."""
+    g = torch.Generator().manual_seed(77)
+    B, N = 3, 1500
+    f1 = F.normalize(torch.randn(B, N, 64, generator=g), dim=-1)
+    f2 = F.normalize(torch.randn(B, N, 64, generator=g), dim=-1)
+    n1 = torch.tensor([1500, 1024, 7], dtype=torch.int32)
+    n2 = torch.tensor([1500, 900, 1500], dtype=torch.int32)
+    with mnn_impl(xf, impl):
+        a = xf._mnn_device(f1.cuda(), n1.cuda(), N, N * 64, f2.cuda(), n2.cuda(), N, N * 64, B, 0.1)
+        b = xf._mnn_device(f1.cuda(), n1.cuda(), N, N * 64, f2.cuda(), n2.cuda(), N, N * 64, B, 0.1, abs_bound=1.0)
+    ca, cb = a[2].tolist(), b[2].tolist()
+    for i in range(B):
+        w0, w1 = orc.mnn_match(f1[i, :n1[i]], f2[i, :n2[i]], 0.1)
+        for got, c in ((a, ca), (b, cb)):
+            check_modulo_ties(f1[i, :n1[i]], f2[i, :n2[i]], (got[0][i, :c[i]].cpu().numpy(), got[1][i, :c[i]].cpu().numpy()),
+                              (w0.numpy(), w1.numpy()))
