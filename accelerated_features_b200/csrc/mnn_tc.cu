@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (tc::elect_one()) {
+    if (T > 0 && tc::elect_one()) {   // no column tiles: nothing may be left in flight when the CTA exits
       // ---------------- TMA producer ----------------
       const int arow = pair * n_pad + row0;
       tc::mbar_expect_tx(a_full, 4 * TC_BOX_BYTES);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
       // S12[i][j] == S21[j][i] bit for bit.
       const int a_sel[3] = {0, dir ? 1 : 0, dir ? 0 : 1};
       const int b_sel[3] = {0, dir ? 0 : 1, dir ? 1 : 0};
-      tc::mbar_wait(a_full, 0);
+      if (T > 0) tc::mbar_wait(a_full, 0);   // (nothing was loaded when there are no column tiles)
       for (int t = 0; t < T; ++t) {
         const int s = t & 1, ph = (t >> 1) & 1;
         tc::mbar_wait(&b_full[s], ph);
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(TC1_THREADS, 1) mnn_tc_once_kernel(const __gri
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (tc::elect_one()) {
+    if (T > 0 && tc::elect_one()) {   // no column tiles: nothing may be left in flight when the CTA exits
       // ---------------- TMA producer ----------------
       const int arow = pair * n_pad + row0;
       tc::mbar_expect_tx(a_full, 4 * TC_BOX_BYTES);
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(TC1_THREADS, 1) mnn_tc_once_kernel(const __gri
       // K-blocks of x.y = hi.hi + hi.lo + lo.hi, taken from the [hi | lo] boxes of the two operands
       constexpr int a_sel[3] = {0, 0, 1};
       constexpr int b_sel[3] = {0, 1, 0};
-      tc::mbar_wait(a_full, 0);
+      if (T > 0) tc::mbar_wait(a_full, 0);   // (nothing was loaded when there are no column tiles)
       for (int t = 0; t < T; ++t) {
         const int s = t & 1, ph = (t >> 1) & 1;
         tc::mbar_wait(&b_full[s], ph);
@@ -609,7 +609,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (tc::elect_one()) {
+    if (T > 0 && tc::elect_one()) {   // no column tiles: nothing may be left in flight when the CTA exits
       // ---------------- TMA producer (both CTAs; bytes are reported to the leader's barriers) ----------------
       const uint32_t a_full_l = tc::mapa_rank(tc::smem_u32(a_full), 0);
       const int arow = pair * n_pad + row0;
@@ -637,7 +637,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       // S12[i][j] == S21[j][i] bit for bit.
       const int a_sel[3] = {0, dir ? 1 : 0, dir ? 0 : 1};
       const int b_sel[3] = {0, dir ? 0 : 1, dir ? 1 : 0};
-      tc::mbar_wait_cluster(a_full, 0);
+      if (T > 0) tc::mbar_wait_cluster(a_full, 0);   // (nothing was loaded when there are no column tiles)
       for (int t = 0; t < T; ++t) {
         const int s = t & 1;
         tc::mbar_wait_cluster(&b_full[s], (t >> 1) & 1);
