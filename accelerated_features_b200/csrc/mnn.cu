@@ -243,6 +243,7 @@ extern "C" int xfeat_mnn_match_bounded(const float* d_f1, const int32_t* d_n1, i
   XF_REQUIRE(((uintptr_t)d_f1 % 16) == 0 && ((uintptr_t)d_f2 % 16) == 0 && stride1 % 4 == 0 && stride2 % 4 == 0,
              "mnn_match: descriptors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (!(abs_bound > 0.f) || !isfinite(abs_bound)) abs_bound = 0.f;   // no usable bound: measure max |x| on the device
   if (xf::g_mnn_impl >= 1) {
     unsigned long long *b12 = nullptr, *b21 = nullptr;
     float* inv_s2 = nullptr;
