@@ -1,6 +1,9 @@
 // C-ABI glue: context, error reporting and the backbone schedule (XFeatModel.forward, model.py:123-154).
 #include <stdarg.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -10,6 +13,21 @@ namespace xf {
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
 int g_conv_impl = 2;  // 0 = fp32 CUDA-core convs everywhere, 1 = tcgen05 for the 64->64 stride-1 layers (default)
+
+// (device, kernel) -> largest dynamic shared-memory size opted into so far
+int ensure_dyn_smem(const void* func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  int dev = 0;
+  XF_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = done[std::make_pair(dev, func)];
+  if (bytes > cur) {
+    XF_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
+  return XF_OK;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -59,7 +77,8 @@ extern "C" int xfeat_create(xfeat_ctx** out, int device, const float* packed_hos
   XF_REQUIRE(out && packed_host, "create: null pointer");
   const xf::LayerTable t = xf::make_layer_table();
   XF_REQUIRE(n_floats == t.total, "create: packed blob has %zu floats, expected %zu", n_floats, t.total);
-  XF_CUDA(cudaSetDevice(device));
+  xf::DeviceGuard guard(device);   // the caller's current device is restored on every return path
+  XF_REQUIRE(guard.ok, "create: cudaSetDevice(%d) failed", device);
   cudaDeviceProp prop;
   XF_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
@@ -100,7 +119,7 @@ extern "C" int xfeat_get_conv_impl(void) { return xf::g_conv_impl; }
 
 extern "C" void xfeat_destroy(xfeat_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  xf::DeviceGuard guard(ctx->device);
   if (ctx->d_weights) cudaFree(ctx->d_weights);
   if (ctx->d_tcw) cudaFree(ctx->d_tcw);
   free(ctx->h_weights);

@@ -40,6 +40,29 @@ extern unsigned long long g_launches;
     }                               \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE (per-context) attribute: remembered per (current device,
+// kernel), so a second XFeat(device=1) in the same process sets it again there (api.cu).
+int ensure_dyn_smem(const void* func, size_t bytes);
+#define XF_DYN_SMEM(kernel, bytes)                                                   \
+  do {                                                                               \
+    int _rc = xf::ensure_dyn_smem((const void*)(kernel), (size_t)(bytes));           \
+    if (_rc != XF_OK) return _rc;                                                    \
+  } while (0)
+
+// cudaSetDevice(dev) for the scope, then back to whatever the caller had current (xfeat_create / xfeat_destroy must not
+// change the caller's device as a side effect).
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

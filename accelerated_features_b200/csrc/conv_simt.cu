@@ -183,11 +183,7 @@ static int launch_cfg(const float* in, const float* w, const float* bias, float*
                       cudaStream_t st, const int* n_live = nullptr, __half* out_split = nullptr) {
   const int Ho = (C::KS == 3) ? (Hi + 2 - 3) / C::S + 1 : Hi / C::S;
   const int Wo = (C::KS == 3) ? (Wi + 2 - 3) / C::S + 1 : Wi / C::S;
-  static bool attr_done = false;
-  if (!attr_done) {
-    XF_CUDA(cudaFuncSetAttribute(conv_simt_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    attr_done = true;
-  }
+  XF_DYN_SMEM(conv_simt_kernel<C>, C::SMEM);
   XF_REQUIRE(B <= 65535, "conv: batch too large for grid.z");
   dim3 grid(cdiv(Ho, C::TH) * cdiv(Wo, C::TW), C::COUT / C::CT, B);
   conv_simt_kernel<C><<<grid, C::THREADS, C::SMEM, st>>>(in, w, bias, out, Hi, Wi, Ho, Wo, n_live, out_split);

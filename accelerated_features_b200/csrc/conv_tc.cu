@@ -633,11 +633,7 @@ static void pick_tile(int H, int W, int& tw_log2) {
 template <int KS, int CINP, int NOUT>
 static int launch_tc_cfg(const ConvTcParams& P, int grid, cudaStream_t st) {
   using C = ConvTcCfg<KS, CINP, NOUT>;
-  static bool attr = false;
-  if (!attr) {
-    XF_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, CINP, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    attr = true;
-  }
+  XF_DYN_SMEM((conv_tc_kernel<KS, CINP, NOUT>), C::SMEM);
   conv_tc_kernel<KS, CINP, NOUT><<<grid, CT_THREADS2, C::SMEM, st>>>(P);
   XF_LAUNCH_CHECK();
   return XF_OK;
@@ -711,12 +707,11 @@ int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int 
     P.n_real = 64;
     const int gx = cdiv(ctx->sm_count, c.ntiles) < n_tiles ? cdiv(ctx->sm_count, c.ntiles) : n_tiles;
     dim3 g2(gx, c.ntiles);
-    static bool attr3 = false, attr1 = false;
     if (sp.ks == 3) {
-      if (!attr3) { XF_CUDA(cudaFuncSetAttribute(conv_tc128_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C128_SMEM)); attr3 = true; }
+      XF_DYN_SMEM(conv_tc128_kernel<3>, C128_SMEM);
       conv_tc128_kernel<3><<<g2, CT_THREADS, C128_SMEM, st>>>(P);
     } else {
-      if (!attr1) { XF_CUDA(cudaFuncSetAttribute(conv_tc128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C128_SMEM)); attr1 = true; }
+      XF_DYN_SMEM(conv_tc128_kernel<1>, C128_SMEM);
       conv_tc128_kernel<1><<<g2, CT_THREADS, C128_SMEM, st>>>(P);
     }
     XF_LAUNCH_CHECK();

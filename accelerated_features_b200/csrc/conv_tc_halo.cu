@@ -346,25 +346,13 @@ int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split,
   P.div_x = make_fastdiv((unsigned)cdiv(W, P.TW));
   const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
   if (c64) {
-    static bool attr = false;
-    if (!attr) {
-      XF_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HaloCfg<64, 64>::SMEM));
-      attr = true;
-    }
+    XF_DYN_SMEM((conv_tc_halo_kernel<64, 64>), (HaloCfg<64, 64>::SMEM));
     conv_tc_halo_kernel<64, 64><<<grid, CH_THREADS, HaloCfg<64, 64>::SMEM, st>>>(P);
   } else if (c32) {
-    static bool attr = false;
-    if (!attr) {
-      XF_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HaloCfg<32, 32>::SMEM));
-      attr = true;
-    }
+    XF_DYN_SMEM((conv_tc_halo_kernel<32, 32>), (HaloCfg<32, 32>::SMEM));
     conv_tc_halo_kernel<32, 32><<<grid, CH_THREADS, HaloCfg<32, 32>::SMEM, st>>>(P);
   } else {
-    static bool attr = false;
-    if (!attr) {
-      XF_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HaloCfg<8, 8>::SMEM));
-      attr = true;
-    }
+    XF_DYN_SMEM((conv_tc_halo_kernel<8, 8>), (HaloCfg<8, 8>::SMEM));
     conv_tc_halo_kernel<8, 8><<<grid, CH_THREADS, HaloCfg<8, 8>::SMEM, st>>>(P);
   }
   XF_LAUNCH_CHECK();

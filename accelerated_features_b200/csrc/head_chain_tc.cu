@@ -319,12 +319,11 @@ int launch_head_chain(const xfeat_ctx* ctx, int mode, const __half* in_split, in
   const int grid = n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count;
   const size_t smem0 = 1024 + (((size_t)3 * 2 * HC_WBOX + 2 * 80 * 128 + 1023) & ~(size_t)1023) + 4 * (size_t)HC_ABOX + 2048;
   const size_t smem1 = 1024 + (((size_t)2 * 2 * HC_WBOX + 2 * 16 * 128 + 1023) & ~(size_t)1023) + 4 * (size_t)HC_ABOX + 2048;
-  static bool a0 = false, a1 = false;
   if (mode == 0) {
-    if (!a0) { XF_CUDA(cudaFuncSetAttribute(head_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)); a0 = true; }
+    XF_DYN_SMEM(head_chain_kernel<0>, smem0);
     head_chain_kernel<0><<<grid, HC_THREADS, smem0, st>>>(P);
   } else {
-    if (!a1) { XF_CUDA(cudaFuncSetAttribute(head_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)); a1 = true; }
+    XF_DYN_SMEM(head_chain_kernel<1>, smem1);
     head_chain_kernel<1><<<grid, HC_THREADS, smem1, st>>>(P);
   }
   XF_LAUNCH_CHECK();

@@ -141,8 +141,9 @@ __global__ void __launch_bounds__(MNN_THREADS) mnn_scan_kernel(const float* __re
 // One CTA per pair: mutual test + threshold + ordered compaction.
 __global__ void __launch_bounds__(1024) mnn_finalize_kernel(const unsigned long long* __restrict__ row_best,
                                                             const unsigned long long* __restrict__ col_best,
-                                                            const int* __restrict__ n1p, int n1_max, int n2_max,
-                                                            float min_cossim, const float* __restrict__ val_scale,
+                                                            const int* __restrict__ n1p, const int* __restrict__ n2p,
+                                                            int n1_max, int n2_max, float min_cossim,
+                                                            const float* __restrict__ val_scale,
                                                             long long* __restrict__ idx0,
                                                             long long* __restrict__ idx1, int* __restrict__ n_matches) {
   using Scan = cub::BlockScan<int, 1024>;
@@ -177,7 +178,9 @@ __global__ void __launch_bounds__(1024) mnn_finalize_kernel(const unsigned long 
     if (threadIdx.x == 0) s_base = base + total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) n_matches[pair] = s_base;
+  // a negative count is xfeat_detect_sparse's overflow indicator (XF_N_OVERFLOW): it propagates instead of reading as "no matches"
+  const bool overflow = (n1p && n1p[pair] < 0) || (n2p && n2p[pair] < 0);
+  if (threadIdx.x == 0) n_matches[pair] = overflow ? -1 : s_base;
 }
 
 __global__ void __launch_bounds__(256) gather_matches_kernel(const float* __restrict__ k0, const float* __restrict__ k1,
@@ -250,7 +253,7 @@ extern "C" int xfeat_mnn_match_bounded(const float* d_f1, const int32_t* d_n1, i
     int rc = xf::launch_mnn_tc(d_f1, d_n1, n1_max, stride1, d_f2, d_n2, n2_max, stride2, batch, d_ws, ws_bytes, &b12, &b21,
                                &inv_s2, st, xf::g_mnn_impl == 2 ? 1 : (xf::g_mnn_impl == 3 ? 2 : 0), abs_bound);
     if (rc) return rc;
-    xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(b12, b21, d_n1, n1_max, n2_max, min_cossim, inv_s2, (long long*)d_idx0,
+    xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(b12, b21, d_n1, d_n2, n1_max, n2_max, min_cossim, inv_s2, (long long*)d_idx0,
                                                     (long long*)d_idx1, d_n_matches);
     XF_LAUNCH_CHECK();
     return XF_OK;
@@ -262,18 +265,14 @@ extern "C" int xfeat_mnn_match_bounded(const float* d_f1, const int32_t* d_n1, i
     xf::set_error("mnn_match: workspace too small (%zu < %zu)", ws_bytes, bump.used());
     return XF_E_WORKSPACE;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    XF_CUDA(cudaFuncSetAttribute(xf::mnn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xf::MNN_SMEM));
-    attr_done = true;
-  }
+  XF_DYN_SMEM(xf::mnn_scan_kernel, xf::MNN_SMEM);
   XF_CUDA(cudaMemsetAsync(ws.row_best, 0, sizeof(unsigned long long) * (size_t)batch * n1_max, st));
   XF_CUDA(cudaMemsetAsync(ws.col_best, 0, sizeof(unsigned long long) * (size_t)batch * n2_max, st));
   dim3 grid(xf::cdiv(n1_max, xf::MNN_BM), batch);
   xf::mnn_scan_kernel<<<grid, xf::MNN_THREADS, xf::MNN_SMEM, st>>>(d_f1, d_n1, n1_max, stride1, d_f2, d_n2, n2_max, stride2,
                                                                   ws.row_best, ws.col_best);
   XF_LAUNCH_CHECK();
-  xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(ws.row_best, ws.col_best, d_n1, n1_max, n2_max, min_cossim, nullptr,
+  xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(ws.row_best, ws.col_best, d_n1, d_n2, n1_max, n2_max, min_cossim, nullptr,
                                                   (long long*)d_idx0, (long long*)d_idx1, d_n_matches);
   XF_LAUNCH_CHECK();
   return XF_OK;

@@ -818,23 +818,15 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
   int rc;
   if ((rc = make_map(&maps.m1, ws.f1s, (uint64_t)batch * n_pad))) return rc;
   if ((rc = make_map(&maps.m2, ws.f2s, (uint64_t)batch * n_pad))) return rc;
-  static bool attr_done = false;
-  if (!attr_done) {
-    XF_CUDA(cudaFuncSetAttribute(mnn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    XF_CUDA(cudaFuncSetAttribute(mnn_tc_once_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC1_SMEM));
-    attr_done = true;
-  }
+  XF_DYN_SMEM(mnn_tc_kernel, TC_SMEM);
+  XF_DYN_SMEM(mnn_tc_once_kernel, TC1_SMEM);
   XF_CUDA(cudaMemsetAsync(ws.best12, 0, sizeof(unsigned long long) * (size_t)batch * n1_max, st));
   *inv_s2 = ws.inv_s2;
   *best12 = ws.best12;
   *best21 = ws.best21;
   XF_CUDA(cudaMemsetAsync(ws.best21, 0, sizeof(unsigned long long) * (size_t)batch * n2_max, st));
   if (once == 2) {   // CTA-pair kernel (cta_group::2)
-    static bool attr2 = false;
-    if (!attr2) {
-      XF_CUDA(cudaFuncSetAttribute(mnn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
-      attr2 = true;
-    }
+    XF_DYN_SMEM(mnn_tc2_kernel, TC2_SMEM);
     dim3 grid2(n_pad / TC_ROWS, batch, 2);   // even by construction (n_pad is a multiple of 512): clusters of 2 along x
     mnn_tc2_kernel<<<grid2, TC_THREADS, TC2_SMEM, st>>>(maps, n1, n1_max, n2, n2_max, n_pad, ws.best12, ws.best21);
     XF_LAUNCH_CHECK();

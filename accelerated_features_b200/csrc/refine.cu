@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int* __restrict
   __syncthreads();
   for (int i0 = 0; i0 < n; i0 += 1024) {
     const int i = i0 + threadIdx.x;
-    const int c = (i < n) ? min(counts[i], cap) : 0;
+    const int c = (i < n) ? max(0, min(counts[i], cap)) : 0;
     int off, total;
     Scan(tmp).ExclusiveSum(c, off, total);
     const int base = s_base;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) refine_gather_kernel(const float* __restr
                                                             const long long* __restrict__ idx1,
                                                             const int* __restrict__ n_matches,
                                                             const int* __restrict__ offsets, int batch, int n_max,
-                                                            float* __restrict__ X) {
+                                                            int n1_max, float* __restrict__ X) {
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= (int64_t)batch * n_max) return;
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) refine_gather_kernel(const float* __restr
   const int64_t row = offsets[pair] + m;
   const long long a = idx0[wid], b = idx1[wid];
   const float2 u = __ldg(reinterpret_cast<const float2*>(d0 + ((int64_t)pair * n_max + a) * 64) + lane);
-  const float2 v = __ldg(reinterpret_cast<const float2*>(d1 + ((int64_t)pair * n_max + b) * 64) + lane);
+  const float2 v = __ldg(reinterpret_cast<const float2*>(d1 + ((int64_t)pair * n1_max + b) * 64) + lane);
   reinterpret_cast<float2*>(X + row * 128)[lane] = u;
   reinterpret_cast<float2*>(X + row * 128 + 64)[lane] = v;
 }
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) refine_finish_kernel(const float* __restr
                                                             const long long* __restrict__ idx1,
                                                             const int* __restrict__ n_matches,
                                                             const int* __restrict__ offsets, int batch, int n_max,
-                                                            float fine_conf, float* __restrict__ tmp,
+                                                            int n1_max, float fine_conf, float* __restrict__ tmp,
                                                             int* __restrict__ keep) {
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) refine_finish_kernel(const float* __restr
     const long long a = idx0[wid], b = idx1[wid];
     const float scale = __ldg(sc0 + (int64_t)pair * n_max + a);
     const float2 p0 = __ldg(reinterpret_cast<const float2*>(k0) + (int64_t)pair * n_max + a);
-    const float2 p1 = __ldg(reinterpret_cast<const float2*>(k1) + (int64_t)pair * n_max + b);
+    const float2 p1 = __ldg(reinterpret_cast<const float2*>(k1) + (int64_t)pair * n1_max + b);
     float* t = tmp + wid * 4;
     t[0] = p0.x + (sx / s) * scale;  // mkpts_0 += offsets * sc0 (xfeat.py:319)
     t[1] = p0.y + (sy / s) * scale;
@@ -141,6 +141,18 @@ static void carve_refine(Bump& bump, int batch, int n_max, RefineWs& ws) {
   ws.keep = bump.take<int>(cap);
 }
 
+// fine_matcher (model.py:97-111): 128 -> 512 -> 512 -> 512 -> 512 -> 64 on `rows_cap` rows of X (row-major, 128 floats);
+// n_live (device, may be null) = number of live rows: tiles past it exit immediately.
+int launch_fine_mlp(const xfeat_ctx* ctx, const float* X, int rows_cap, const int* n_live, float* actA, float* actB,
+                    float* logits, cudaStream_t st) {
+  int rc;
+  if ((rc = launch_conv_layer(ctx, L_FM_0, X, IN_NHWC, 1, 1, rows_cap, actA, st, n_live))) return rc;
+  if ((rc = launch_conv_layer(ctx, L_FM_1, actA, IN_NHWC, 1, 1, rows_cap, actB, st, n_live))) return rc;
+  if ((rc = launch_conv_layer(ctx, L_FM_2, actB, IN_NHWC, 1, 1, rows_cap, actA, st, n_live))) return rc;
+  if ((rc = launch_conv_layer(ctx, L_FM_3, actA, IN_NHWC, 1, 1, rows_cap, actB, st, n_live))) return rc;
+  return launch_conv_layer(ctx, L_FM_4, actB, IN_NHWC, 1, 1, rows_cap, logits, st, n_live);
+}
+
 }  // namespace xf
 
 extern "C" size_t xfeat_refine_workspace_bytes(int batch, int n_max) {
@@ -152,12 +164,12 @@ extern "C" size_t xfeat_refine_workspace_bytes(int batch, int n_max) {
 
 extern "C" int xfeat_refine(xfeat_ctx* ctx, const float* d_desc0, const float* d_desc1, const float* d_kpts0,
                             const float* d_kpts1, const float* d_scales0, const int64_t* d_idx0, const int64_t* d_idx1,
-                            const int32_t* d_n_matches, int batch, int n_max, float fine_conf, float* d_matches,
+                            const int32_t* d_n_matches, int batch, int n_max, int n1_max, float fine_conf, float* d_matches,
                             int32_t* d_n_refined, void* d_ws, size_t ws_bytes, void* stream) {
   XF_REQUIRE(ctx && d_desc0 && d_desc1 && d_kpts0 && d_kpts1 && d_scales0 && d_idx0 && d_idx1 && d_n_matches &&
                  d_matches && d_n_refined && d_ws,
              "refine: null pointer");
-  XF_REQUIRE(batch > 0 && batch <= 65535 && n_max > 0 && (int64_t)batch * n_max < (1ll << 31), "refine: bad sizes");
+  XF_REQUIRE(batch > 0 && batch <= 65535 && n_max > 0 && n1_max > 0 && (int64_t)batch * n_max < (1ll << 31), "refine: bad sizes");
   XF_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   xf::Bump bump(d_ws, ws_bytes);
@@ -172,17 +184,13 @@ extern "C" int xfeat_refine(xfeat_ctx* ctx, const float* d_desc0, const float* d
   xf::scan_counts_kernel<<<1, 1024, 0, st>>>(d_n_matches, batch, n_max, ws.offsets);
   XF_LAUNCH_CHECK();
   xf::refine_gather_kernel<<<wblocks, 256, 0, st>>>(d_desc0, d_desc1, (const long long*)d_idx0, (const long long*)d_idx1,
-                                                    d_n_matches, ws.offsets, batch, n_max, ws.X);
+                                                    d_n_matches, ws.offsets, batch, n_max, n1_max, ws.X);
   XF_LAUNCH_CHECK();
   const int* n_live = ws.offsets + batch;
   int rc;
-  if ((rc = xf::launch_conv_layer(ctx, xf::L_FM_0, ws.X, xf::IN_NHWC, 1, 1, (int)cap, ws.actA, st, n_live))) return rc;
-  if ((rc = xf::launch_conv_layer(ctx, xf::L_FM_1, ws.actA, xf::IN_NHWC, 1, 1, (int)cap, ws.actB, st, n_live))) return rc;
-  if ((rc = xf::launch_conv_layer(ctx, xf::L_FM_2, ws.actB, xf::IN_NHWC, 1, 1, (int)cap, ws.actA, st, n_live))) return rc;
-  if ((rc = xf::launch_conv_layer(ctx, xf::L_FM_3, ws.actA, xf::IN_NHWC, 1, 1, (int)cap, ws.actB, st, n_live))) return rc;
-  if ((rc = xf::launch_conv_layer(ctx, xf::L_FM_4, ws.actB, xf::IN_NHWC, 1, 1, (int)cap, ws.logits, st, n_live))) return rc;
+  if ((rc = xf::launch_fine_mlp(ctx, ws.X, (int)cap, n_live, ws.actA, ws.actB, ws.logits, st))) return rc;
   xf::refine_finish_kernel<<<wblocks, 256, 0, st>>>(ws.logits, d_kpts0, d_kpts1, d_scales0, (const long long*)d_idx0,
-                                                    (const long long*)d_idx1, d_n_matches, ws.offsets, batch, n_max,
+                                                    (const long long*)d_idx1, d_n_matches, ws.offsets, batch, n_max, n1_max,
                                                     fine_conf, ws.tmp, ws.keep);
   XF_LAUNCH_CHECK();
   xf::refine_compact_kernel<<<batch, 1024, 0, st>>>(ws.tmp, ws.keep, d_n_matches, n_max, d_matches, d_n_refined);

@@ -405,8 +405,9 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
   const bool live = slot < total;
   const int64_t sl = live ? slot : total - 1;   // keep the whole warp converged for the shuffles below
   const int b = (int)(sl / top_k), r = (int)(sl - (int64_t)b * top_k);
-  const int nv = min(min(n_keep[b], cap), top_k);
-  if (live && r == 0 && l16 == 0) n_valid[b] = nv;
+  const int nk = n_keep[b];
+  const int nv = nk > cap ? 0 : min(nk, top_k);   // candidate overflow: nothing is trusted, n_valid = XF_N_OVERFLOW (header)
+  if (live && r == 0 && l16 == 0) n_valid[b] = nk > cap ? -1 : nv;
   const bool valid = r < nv;
   float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
   int x = 0, y = 0;
@@ -455,8 +456,9 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
   unsigned short* sOrder = reinterpret_cast<unsigned short*>(sKey + top_k);            // [top_k]
   __shared__ int sHist[SAMPLE_MAX_ROWS];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int nv = min(min(n_keep[b], cap), top_k);
-  if (tid == 0) n_valid[b] = nv;
+  const int nk = n_keep[b];
+  const int nv = nk > cap ? 0 : min(nk, top_k);   // candidate overflow: nothing is trusted, n_valid = XF_N_OVERFLOW (header)
+  if (tid == 0) n_valid[b] = nk > cap ? -1 : nv;
   for (int i = tid; i < SAMPLE_MAX_ROWS; i += SAMPLE_THREADS) sHist[i] = 0;
   __syncthreads();
   for (int r = tid; r < nv; r += SAMPLE_THREADS) {
@@ -612,11 +614,7 @@ extern "C" int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const f
   static const bool force_generic = getenv("XFEAT_SAMPLE_GENERIC") != nullptr;
   if (!force_generic && B >= 32 && top_k <= xf::SAMPLE_MAX_K && Hm <= xf::SAMPLE_MAX_ROWS) {
     const size_t smem = (size_t)top_k * (sizeof(unsigned long long) + sizeof(unsigned short));
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      XF_CUDA(cudaFuncSetAttribute(xf::sample_desc_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
+    XF_DYN_SMEM(xf::sample_desc_sorted_kernel, smem);
     xf::sample_desc_sorted_kernel<<<B, xf::SAMPLE_THREADS, smem, st>>>(ws.sorted, ws.n_keep, d_feats, ws.den, H, W, Hm, Wm, cap,
                                                                       top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid,
                                                                       d_kpts_int);

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define XFEAT_ABI_VERSION 1
+#define XFEAT_ABI_VERSION 2
 #if defined(__GNUC__)
 #define XF_API __attribute__((visibility("default")))
 #else
@@ -38,6 +38,11 @@ enum {
   XF_E_WORKSPACE = 3,   /* workspace too small */
   XF_E_UNSUPPORTED = 4
 };
+
+/* Per-image / per-pair counts (d_n_valid, d_n_matches) carry this value when the NMS candidate buffer of that image
+ * overflowed (more than H*W/4 maxima above the threshold: equal-valued plateaus pass the reference's `x == local_max` test,
+ * xfeat.py:252, so there is no hard bound): nothing is returned for the image instead of an arbitrary subset. */
+#define XF_N_OVERFLOW (-1)
 
 /* pixel formats accepted by xfeat_preprocess */
 enum { XF_DTYPE_F32 = 0, XF_DTYPE_U8 = 1 };
@@ -98,7 +103,8 @@ XF_API size_t xfeat_sparse_workspace_bytes(int B, int H, int W, int top_k);
  * F.normalize(dim=-1), keypoint rescale and the `scores > 0` filter (xfeat.py:70-103).
  * Outputs (fixed capacity top_k per image, sorted by score descending, ties by raster index ascending):
  *   d_kpts (B,top_k,2) f32 = (x*rw, y*rh); d_scores (B,top_k); d_desc (B,top_k,64); d_n_valid (B) int32 = number
- *   of leading entries with score > 0; d_n_cand (B) int32 = number of NMS maxima above threshold (before the
+ *   of leading entries with score > 0, or XF_N_OVERFLOW when more than H*W/4 candidates with a positive score were found
+ *   (all outputs of that image are then zero-filled); d_n_cand (B) int32 = number of NMS maxima above threshold (before the
  *   score filter; for parity checks, may be NULL); d_kpts_int (B,top_k,2) int32 optional. Entries past n_valid
  *   are zero-filled. */
 XF_API int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const float* d_heat, const float* d_reliability,
@@ -130,7 +136,8 @@ XF_API size_t xfeat_mnn_workspace_bytes(int batch, int n1_max, int n2_max);
  * d_f2 + b*stride2 (n2[b] x 64); strides in floats.  d_n1 / d_n2: device int32 per-pair counts (NULL = n1_max /
  * n2_max for every pair).  argmax ties resolve to the lowest index, as torch.max / argmax on CPU.
  * min_cossim <= 0 disables the threshold (reference semantics).
- * Outputs per pair at capacity n1_max: d_idx0, d_idx1 (batch, n1_max) int64 (idx0 ascending), d_n_matches (batch).
+ * Outputs per pair at capacity n1_max: d_idx0, d_idx1 (batch, n1_max) int64 (idx0 ascending), d_n_matches (batch);
+ * a negative d_n1 / d_n2 entry (XF_N_OVERFLOW from xfeat_detect_sparse) gives d_n_matches = XF_N_OVERFLOW for that pair.
  * Never materialises the similarity matrix. */
 XF_API int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_max, int64_t stride1,
                     const float* d_f2, const int32_t* d_n2, int n2_max, int64_t stride2,
@@ -153,14 +160,48 @@ XF_API int xfeat_gather_matches(const float* d_kpts0, const float* d_kpts1, int 
 
 XF_API size_t xfeat_refine_workspace_bytes(int batch, int n_max);
 /* replaces: XFeat.refine_matches + fine_matcher + subpix_softmax2d (xfeat.py:292-325, model.py:97-111), for all
- * pairs of the batch at once.  Inputs: un-normalised coarse descriptors d_desc0/1 (batch,n_max,64), keypoints
- * d_kpts0/1 (batch,n_max,2), d_scales0 (batch,n_max), coarse matches d_idx0/d_idx1 (batch,n_max) + d_n_matches.
- * Output d_matches (batch,n_max,4) = (x0+dx*s, y0+dy*s, x1, y1) for rows with conf > fine_conf, order preserved;
+ * pairs of the batch at once.  Inputs: un-normalised coarse descriptors d_desc0 (batch,n_max,64) / d_desc1 (batch,n1_max,64),
+ * keypoints d_kpts0 (batch,n_max,2) / d_kpts1 (batch,n1_max,2), d_scales0 (batch,n_max), coarse matches d_idx0/d_idx1
+ * (batch,n_max) + d_n_matches (the two image sets may yield different numbers of coarse features, as reference batch_match
+ * allows).  Output d_matches (batch,n_max,4) = (x0+dx*s, y0+dy*s, x1, y1) for rows with conf > fine_conf, order preserved;
  * d_n_refined (batch). */
 XF_API int xfeat_refine(xfeat_ctx* ctx, const float* d_desc0, const float* d_desc1, const float* d_kpts0,
                  const float* d_kpts1, const float* d_scales0, const int64_t* d_idx0, const int64_t* d_idx1,
-                 const int32_t* d_n_matches, int batch, int n_max, float fine_conf, float* d_matches,
+                 const int32_t* d_n_matches, int batch, int n_max, int n1_max, float fine_conf, float* d_matches,
                  int32_t* d_n_refined, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Stand-alone forms of the reference's helper methods (the same arithmetic runs fused inside the stage entry points)
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* replaces: XFeat.get_kpts_heatmap (xfeat.py:242-247).  d_logits (B,65,Hc,Wc) NCHW fp32 -> d_heat (B,1,8*Hc,8*Wc):
+ * softmax(logits * softmax_temp) over the 65 channels, dustbin dropped, heat[b,8h+i,8w+j] = p[b,8i+j,h,w]. */
+XF_API int xfeat_kpts_heatmap(const float* d_logits, int B, int Hc, int Wc, float softmax_temp, float* d_heat, void* stream);
+
+/* replaces: XFeat.NMS (xfeat.py:249-263): pos = (x == MaxPool2d(kernel_size, stride 1, pad kernel_size/2)(x)) & (x > threshold),
+ * positions (x, y) int64 in raster order.  Two calls, as the reference's own nonzero() needs the count on the host:
+ * xfeat_nms_count fills d_counts (B) int32; the caller sizes d_pos (B, pos_cap, 2) (zero-initialised = the reference's
+ * padding, pos_cap = max count) and xfeat_nms_write fills it.  d_ws: xfeat_nms_workspace_bytes, kept between the calls. */
+XF_API size_t xfeat_nms_workspace_bytes(int B, int H, int W);
+XF_API int xfeat_nms_count(const float* d_heat, int B, int H, int W, int kernel_size, float threshold, int32_t* d_counts,
+                           void* d_ws, size_t ws_bytes, void* stream);
+XF_API int xfeat_nms_write(const float* d_heat, int B, int H, int W, int kernel_size, float threshold, int64_t* d_pos,
+                           int pos_cap, void* d_ws, size_t ws_bytes, void* stream);
+
+/* replaces: InterpolateSparse2d.forward (interpolator.py:17-33): grid = 2*pos/(W-1,H-1) - 1, F.grid_sample(align_corners=False,
+ * zeros padding); mode 0 = nearest, 1 = bilinear, 2 = bicubic.  d_x (B,C,Hm,Wm) NCHW fp32, d_pos (B,N,2) fp32 (x,y) in the
+ * H x W frame, d_out (B,N,C). */
+XF_API int xfeat_interpolate_sparse(const float* d_x, const float* d_pos, int B, int C, int Hm, int Wm, int N, int H, int W,
+                                    int mode, float* d_out, void* stream);
+
+/* replaces: XFeat.subpix_softmax2d (xfeat.py:292-304) for 8x8 maps: d_maps (n,64) -> d_out (n,2) = E[(x-4, y-4)] under
+ * softmax(temp * map). */
+XF_API int xfeat_subpix_softmax2d(const float* d_maps, int64_t n, float temp, float* d_out, void* stream);
+
+/* replaces: XFeatModel.fine_matcher (model.py:97-111; Linear + BatchNorm1d(affine=False) folded + ReLU x4, Linear):
+ * d_x (n,128) -> d_out (n,64) logits. */
+XF_API size_t xfeat_fine_matcher_workspace_bytes(int n);
+XF_API int xfeat_fine_matcher(xfeat_ctx* ctx, const float* d_x, int n, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Test hook: run one folded conv layer of the packed table (index into csrc/layers.h) through the generic
  * kernels. in (B,Hi,Wi,Cin) NHWC -> out (B,Ho,Wo,Cout). */

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(lib_path):
 def test_library_loads_and_reports(lib_path):
     from accelerated_features_b200 import _lib, weights
     lib = _lib.load()
-    assert lib.xfeat_abi_version() == 1
+    assert lib.xfeat_abi_version() == _lib.ABI_VERSION == 2
     blob = weights.pack_weights(weights.load_state_dict(weights.DEFAULT_WEIGHTS))
     assert blob.dtype == np.float32 and blob.size == lib.xfeat_packed_weight_floats()
     assert lib.xfeat_launch_count() == 0

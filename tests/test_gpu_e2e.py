@@ -15,47 +15,84 @@ def xf():
     return XFeat()
 
 
-def kp_set(kp):
-    return {(float(x), float(y)) for x, y in np.asarray(kp)}
+from tests.parity_util import (assert_keypoints_exact_modulo_ties, assert_matches_exact_modulo_ties, kp_set, match_set,  # noqa: E402
+                               record)
+
+
+def _check_detect(name, got, want, st, top_k, rw=1.0, rh=1.0):
+    """detectAndCompute output of one batch vs the oracle: exact keypoint sets modulo enumerated near-ties, scores and
+    descriptors within 1e-3 (north_star) on the common keypoints.  Returns per-image (n_got, n_want, n_diff)."""
+    stats = []
+    for b in range(len(want)):
+        g, w = got[b], want[b]
+        gk, wk = g["keypoints"].cpu().numpy(), w["keypoints"].numpy()
+        nd = assert_keypoints_exact_modulo_ties(f"{name}[{b}]", gk, wk, st, b, top_k, rw, rh)
+        gi = {(float(x), float(y)): i for i, (x, y) in enumerate(gk)}
+        wi = {(float(x), float(y)): i for i, (x, y) in enumerate(wk)}
+        common = sorted(set(gi) & set(wi))
+        derr = serr = 0.0
+        if common:
+            ia = np.array([gi[c] for c in common]); ib = np.array([wi[c] for c in common])
+            derr = float(np.abs(g["descriptors"].cpu().numpy()[ia] - w["descriptors"].numpy()[ib]).max())
+            serr = float(np.abs(g["scores"].cpu().numpy()[ia] - w["scores"].numpy()[ib]).max())
+        assert derr < 1e-3 and serr < 1e-3, (name, b, derr, serr)
+        s = g["scores"].cpu().numpy()
+        assert np.all(s[:-1] >= s[1:]) and np.all(s > 0)
+        stats.append({"got": len(gk), "want": len(wk), "differing": nd, "desc_err": derr, "score_err": serr})
+    return stats
 
 
 def test_detect_and_compute_assets(xf, oracle_state, assets_vga):
     ref, tgt = assets_vga
     x = torch.cat([orc.parse_input(ref), orc.parse_input(tgt)], 0)
-    want = orc.detect_and_compute(oracle_state, x, 4096)
+    want, st = orc.detect_and_compute(oracle_state, x, 4096, return_stages=True)
     got = xf.detectAndCompute(x, top_k=4096)
     assert len(got) == 2
-    for b in range(2):
-        g, w = got[b], want[b]
+    for g in got:
         assert g["keypoints"].dtype == torch.float32 and g["keypoints"].shape[1] == 2
         assert g["descriptors"].shape[1] == 64 and g["scores"].ndim == 1
-        gk, wk = g["keypoints"].cpu().numpy(), w["keypoints"].numpy()
-        common = kp_set(gk) & kp_set(wk)
-        frac = len(common) / len(wk)
-        print(f"image {b}: {len(gk)} vs {len(wk)} kpts, common {len(common)} ({frac:.4f})")
-        assert frac >= 0.995        # end to end the heat-map differs by fp32 re-association: only threshold/tie cases move
-        # descriptors & scores on the common keypoints: 1e-3 (north_star tolerance)
-        gi = {(float(x), float(y)): i for i, (x, y) in enumerate(gk)}
-        wi = {(float(x), float(y)): i for i, (x, y) in enumerate(wk)}
-        ia = np.array([gi[c] for c in common]); ib = np.array([wi[c] for c in common])
-        derr = np.abs(g["descriptors"].cpu().numpy()[ia] - w["descriptors"].numpy()[ib]).max()
-        serr = np.abs(g["scores"].cpu().numpy()[ia] - w["scores"].numpy()[ib]).max()
-        print(f"   desc max err {derr:.2e}, score max err {serr:.2e}")
-        assert derr < 1e-3 and serr < 1e-3
-        s = g["scores"].cpu().numpy()
-        assert np.all(s[:-1] >= s[1:]) and np.all(s > 0)
+    stats = _check_detect("assets_vga", got, want, st, 4096)
+    record("detectAndCompute_assets_vga", images=stats)
 
 
 def test_match_xfeat_assets_numpy_input(xf, oracle_state, assets_vga, golden):
     ref, tgt = assets_vga
     mk0, mk1 = xf.match_xfeat(ref, tgt, top_k=4096)           # numpy HWC uint8 -> /255 on device
     assert isinstance(mk0, np.ndarray) and mk0.dtype == np.float32 and mk0.shape == mk1.shape and mk0.shape[1] == 2
-    g = golden("g1_sparse_vga.npz")
-    want = {(float(a), float(b), float(c), float(d)) for (a, b), (c, d) in zip(g["mkpts0"], g["mkpts1"])}
-    got = {(float(a), float(b), float(c), float(d)) for (a, b), (c, d) in zip(mk0, mk1)}
-    frac = len(want & got) / len(want)
-    print(f"matches: {len(got)} vs golden {len(want)}, common {len(want & got)} ({frac:.4f})")
-    assert frac >= 0.98
+    g = golden("g1_sparse_vga.npz")                            # produced by the live reference (tools/make_golden.py)
+    want = match_set(g["mkpts0"], g["mkpts1"])
+    got = match_set(mk0, mk1)
+    x = torch.cat([orc.parse_input(ref), orc.parse_input(tgt)], 0)
+    res = orc.detect_and_compute(oracle_state, x, 4096)
+    nd = assert_matches_exact_modulo_ties("match_xfeat_assets", got, want, res[0]["keypoints"].numpy(), res[0]["descriptors"],
+                                          res[1]["keypoints"].numpy(), res[1]["descriptors"])
+    record("match_xfeat_assets_vga", matches=len(got), golden=len(want), differing=nd)
+
+
+def test_randn_vga_vs_oracle(xf, oracle_state):
+    """The bench workload (BASELINE config 2: seed-0 randn VGA, top_k 4096, saturated cut) on 4 pairs, against the oracle:
+    keypoints exact modulo enumerated near-ties (the 4096-cut included), matches exact modulo MNN near-ties."""
+    g = torch.Generator().manual_seed(0)
+    x1 = torch.randn(4, 3, 480, 640, generator=g)
+    x2 = torch.randn(4, 3, 480, 640, generator=g)
+    with torch.inference_mode():
+        w1, st1 = orc.detect_and_compute(oracle_state, x1, 4096, return_stages=True)
+        w2, st2 = orc.detect_and_compute(oracle_state, x2, 4096, return_stages=True)
+    g1 = xf.detectAndCompute(x1, top_k=4096)
+    g2 = xf.detectAndCompute(x2, top_k=4096)
+    s1 = _check_detect("randn_vga_set1", g1, w1, st1, 4096)
+    s2 = _check_detect("randn_vga_set2", g2, w2, st2, 4096)
+    out = xf.match_xfeat_batch(x1, x2, top_k=4096)
+    pairs = []
+    for b in range(4):
+        i0, i1 = orc.mnn_match(w1[b]["descriptors"], w2[b]["descriptors"], -1)
+        want = match_set(w1[b]["keypoints"][i0].numpy(), w2[b]["keypoints"][i1].numpy())
+        got = match_set(*out[b])
+        nd = assert_matches_exact_modulo_ties(f"randn_vga_pair{b}", got, want, w1[b]["keypoints"].numpy(), w1[b]["descriptors"],
+                                              w2[b]["keypoints"].numpy(), w2[b]["descriptors"], s1[b]["differing"],
+                                              s2[b]["differing"])
+        pairs.append({"matches": len(got), "oracle": len(want), "differing": nd})
+    record("randn_vga_bench_workload", set1=s1, set2=s2, pairs=pairs)
 
 
 def test_match_xfeat_batch_equals_single(xf, assets_vga):
@@ -79,7 +116,7 @@ def test_star_assets(xf, oracle_state, assets_vga, golden):
     assert np.array_equal(d["scales"].cpu().numpy(), g["scales"])
     for b in range(2):
         common = kp_set(d["keypoints"][b].cpu().numpy()) & kp_set(g["kp"][b])
-        assert len(common) >= 0.99 * 4095, len(common)
+        assert len(common) >= 4095 - 4, len(common)          # only reliability near-ties at the two top-k cuts may move
     ml = xf.match_xfeat_star(s1, s2, top_k=4096)
     assert isinstance(ml, list) and len(ml) == 2 and ml[0].shape[1] == 4 and ml[0].is_cuda
     for b in range(2):
@@ -89,7 +126,9 @@ def test_star_assets(xf, oracle_state, assets_vga, golden):
         wd = {(float(r[2]), float(r[3])): r[:2] for r in want}
         hit = sum(1 for r in got if (float(r[2]), float(r[3])) in wd and np.abs(wd[(float(r[2]), float(r[3]))] - r[:2]).max() < 0.05)
         print(f"star pair {b}: {len(got)} vs {len(want)} refined, agreeing {hit}")
-        assert hit >= 0.95 * len(want) and abs(len(got) - len(want)) <= 0.05 * len(want)
+        record(f"match_xfeat_star_assets_vga_pair{b}", refined=len(got), golden=len(want), agreeing=hit)
+        # coarse MNN near-ties and conf ~ 0.25 rows are the only admitted differences: a handful of rows at most
+        assert len(want) - hit <= 6 and abs(len(got) - len(want)) <= 6
     a0, a1 = xf.match_xfeat_star(ref, tgt, top_k=4096)         # B == 1 -> numpy pair
     assert isinstance(a0, np.ndarray) and a0.shape == a1.shape and a0.shape[1] == 2
 
@@ -141,19 +180,10 @@ def test_batch32_small_images_vs_oracle(xf, oracle_state):
     """B = 32 routes description through the one-CTA-per-image (spatially ordered) sampler: check it against the oracle."""
     g = torch.Generator().manual_seed(21)
     x = torch.randn(32, 3, 96, 128, generator=g)
-    want = orc.detect_and_compute(oracle_state, x, 300)
+    want, st = orc.detect_and_compute(oracle_state, x, 300, return_stages=True)
     got = xf.detectAndCompute(x, top_k=300)
-    worst = 0.0
-    for b in range(32):
-        gk, wk = got[b]["keypoints"].cpu().numpy(), want[b]["keypoints"].numpy()
-        gi = {(float(a), float(c)): i for i, (a, c) in enumerate(gk)}
-        wi = {(float(a), float(c)): i for i, (a, c) in enumerate(wk)}
-        common = set(gi) & set(wi)
-        assert len(common) >= 0.98 * len(wk), (b, len(common), len(wk))
-        ia = np.array([gi[c] for c in common]); ib = np.array([wi[c] for c in common])
-        worst = max(worst, float(np.abs(got[b]["descriptors"].cpu().numpy()[ia] - want[b]["descriptors"].numpy()[ib]).max()))
-    print(f"B=32 sampler: worst descriptor error {worst:.2e}")
-    assert worst < 1e-3
+    stats = _check_detect("batch32_small", got, want, st, 300)
+    record("batch32_small_images", differing=sum(s["differing"] for s in stats), worst_desc_err=max(s["desc_err"] for s in stats))
 
 
 def test_star_hd_pair_vs_oracle(xf, oracle_state, assets_vga):
@@ -171,7 +201,8 @@ def test_star_hd_pair_vs_oracle(xf, oracle_state, assets_vga):
         wd = {(float(r[2]), float(r[3])): r[:2] for r in w}
         hit = sum(1 for r in g if (float(r[2]), float(r[3])) in wd and np.abs(wd[(float(r[2]), float(r[3]))] - r[:2]).max() < 0.05)
         print(f"HD star pair {b}: {len(g)} vs {len(w)} refined matches, agreeing {hit}")
-        assert hit >= 0.95 * len(w) and abs(len(g) - len(w)) <= 0.05 * len(w) + 2
+        record(f"match_xfeat_star_hd_pair{b}", refined=len(g), oracle=len(w), agreeing=hit)
+        assert len(w) - hit <= 8 and abs(len(g) - len(w)) <= 8
 
 
 @pytest.mark.parametrize("hw", [(32, 32), (64, 96), (600, 800), (200, 328)])
@@ -181,15 +212,7 @@ def test_odd_sizes_vs_oracle(xf, oracle_state, assets_vga, hw):
     H, W = hw
     x = torch.nn.functional.interpolate(torch.cat([orc.parse_input(ref), orc.parse_input(tgt)], 0), size=(H, W), mode="bilinear",
                                         align_corners=False)
-    want = orc.detect_and_compute(oracle_state, x, 512)
+    want, st = orc.detect_and_compute(oracle_state, x, 512, return_stages=True)
     got = xf.detectAndCompute(x, top_k=512)
-    for b in range(2):
-        gk, wk = got[b]["keypoints"].cpu().numpy(), want[b]["keypoints"].numpy()
-        gi = {(float(a), float(c)): i for i, (a, c) in enumerate(gk)}
-        wi = {(float(a), float(c)): i for i, (a, c) in enumerate(wk)}
-        common = set(gi) & set(wi)
-        print(f"{H}x{W} image {b}: {len(gk)} vs {len(wk)} keypoints, common {len(common)}")
-        assert len(common) >= 0.97 * len(wk) - 1
-        if common:
-            ia = np.array([gi[c] for c in common]); ib = np.array([wi[c] for c in common])
-            assert np.abs(got[b]["descriptors"].cpu().numpy()[ia] - want[b]["descriptors"].numpy()[ib]).max() < 1e-3
+    stats = _check_detect(f"odd_{H}x{W}", got, want, st, 512, rw=st["rw"], rh=st["rh"])
+    record(f"odd_size_{H}x{W}", images=stats)

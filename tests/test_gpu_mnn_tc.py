@@ -32,21 +32,33 @@ def mnn_impl(xf, impl):
 
 
 def check_modulo_ties(f1, f2, got, want, eps_rel=3e-6):
+    """Exact equality of the match lists, or every differing pair touches a row / column of S = F1 F2^T whose top-1 / top-2
+    gap is below eps_rel * max|S| (fp32 accumulation noise).  Gaps are computed for the differing rows / columns only, so the
+    check stays cheap at 32k x 32k."""
     g0, g1 = got
     w0, w1 = want
     if np.array_equal(g0, w0) and np.array_equal(g1, w1):
         return 0
-    s = f1.double() @ f2.double().t()
-    eps = eps_rel * float(s.abs().max())
-    r = torch.topk(s, min(2, s.shape[1]), dim=1).values
-    c = torch.topk(s, min(2, s.shape[0]), dim=0).values
-    rgap = (r[:, 0] - r[:, -1]) if s.shape[1] > 1 else torch.full((s.shape[0],), 1e9)
-    cgap = (c[0] - c[-1]) if s.shape[0] > 1 else torch.full((s.shape[1],), 1e9)
+    f1d, f2d = f1.double(), f2.double()
     wset = {(int(a), int(b)) for a, b in zip(w0, w1)}
     gset = {(int(a), int(b)) for a, b in zip(g0, g1)}
-    diff = wset ^ gset
+    diff = sorted(wset ^ gset)
+    assert len(diff) <= 64, f"{len(diff)} differing pairs"
+
+    def gap(v):
+        if v.numel() < 2:
+            return 1e9
+        t = torch.topk(v, 2).values
+        return float(t[0] - t[1])
+
+    gaps, smax = [], 0.0
     for a, b in diff:
-        assert rgap[a] < eps or cgap[b] < eps, f"robust pair ({a},{b}) differs (row gap {float(rgap[a]):.3e}, col gap {float(cgap[b]):.3e}, eps {eps:.3e})"
+        r, c = f1d[a] @ f2d.t(), f1d @ f2d[b]
+        smax = max(smax, float(r.abs().max()), float(c.abs().max()))
+        gaps.append((gap(r), gap(c)))
+    eps = eps_rel * smax
+    for (a, b), (rg, cg) in zip(diff, gaps):
+        assert rg < eps or cg < eps, f"robust pair ({a},{b}) differs (row gap {rg:.3e}, col gap {cg:.3e}, eps {eps:.3e})"
     return len(diff)
 
 
@@ -81,6 +93,20 @@ def test_tc_vs_oracle_sizes(xf, n1, n2, impl):
             got = run(xf, f1, f2, thr)
             nd = check_modulo_ties(f1, f2, got, (w0.numpy(), w1.numpy()))
             assert nd <= max(2, n1 // 500)
+
+
+@pytest.mark.parametrize("n", [8192, 16384, 32768])
+def test_default_impl_vs_oracle_c5_sweep(xf, n):
+    """BASELINE config 5 (MNN sweep 2k..32k): the upper half of the sweep against the oracle, default implementation."""
+    g = torch.Generator().manual_seed(0)
+    f1 = F.normalize(torch.randn(n, 64, generator=g), dim=-1)
+    f2 = F.normalize(torch.randn(n, 64, generator=g), dim=-1)
+    w0, w1 = orc.mnn_match(f1, f2, -1)
+    got = run(xf, f1, f2, -1)
+    nd = check_modulo_ties(f1, f2, got, (w0.numpy(), w1.numpy()))
+    from tests.parity_util import record
+    record(f"mnn_c5_n{n}", mutual=len(got[0]), oracle=len(w0), tie_differences=nd)
+    assert nd <= max(2, n // 2000)
 
 
 @pytest.mark.parametrize("impl", TC_IMPLS)

@@ -294,6 +294,6 @@ def test_resize_vs_oracle(xf, assets_vga):
     x = vga_batch(assets_vga)
     for s in (0.6, 1.3):
         want = F.interpolate(x, scale_factor=s, align_corners=False, mode="bilinear")
-        got = xf._resize(x.cuda(), False, s).cpu()
+        got = xf._resize_scale(x.cuda(), False, s).cpu()
         assert got.shape == want.shape
         assert (got - want).abs().max().item() < 1e-5
