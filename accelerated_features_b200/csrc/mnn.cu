@@ -139,13 +139,17 @@ __global__ void __launch_bounds__(MNN_THREADS) mnn_scan_kernel(const float* __re
 }
 
 // One CTA per pair: mutual test + threshold + ordered compaction.
+// f1 / f2 (optional, with their per-pair strides in floats): when given, the min_cossim test uses the fp32 dot product of the
+// matched rows instead of the packed value (implementation 4 carries approximate values for rows it did not re-score).
 __global__ void __launch_bounds__(1024) mnn_finalize_kernel(const unsigned long long* __restrict__ row_best,
                                                             const unsigned long long* __restrict__ col_best,
                                                             const int* __restrict__ n1p, const int* __restrict__ n2p,
                                                             int n1_max, int n2_max, float min_cossim,
                                                             const float* __restrict__ val_scale,
                                                             long long* __restrict__ idx0,
-                                                            long long* __restrict__ idx1, int* __restrict__ n_matches) {
+                                                            long long* __restrict__ idx1, int* __restrict__ n_matches,
+                                                            const float* __restrict__ f1 = nullptr, int64_t stride1 = 0,
+                                                            const float* __restrict__ f2 = nullptr, int64_t stride2 = 0) {
   using Scan = cub::BlockScan<int, 1024>;
   __shared__ typename Scan::TempStorage tmp;
   __shared__ int s_base;
@@ -164,7 +168,20 @@ __global__ void __launch_bounds__(1024) mnn_finalize_kernel(const unsigned long 
         j = packed_idx(rb);
         const unsigned long long cb = col_best[(int64_t)pair * n2_max + j];
         flag = (cb != 0ull) && (packed_idx(cb) == (uint32_t)i);
-        if (min_cossim > 0.f) flag = flag && (packed_val(rb) * vs > min_cossim);
+        if (flag && min_cossim > 0.f) {
+          float v = packed_val(rb) * vs;
+          if (f1) {
+            const float4* a = reinterpret_cast<const float4*>(f1 + (int64_t)pair * stride1 + (int64_t)i * 64);
+            const float4* b = reinterpret_cast<const float4*>(f2 + (int64_t)pair * stride2 + (int64_t)j * 64);
+            v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float4 x = __ldg(a + k), y = __ldg(b + k);
+              v = fmaf(x.x, y.x, v); v = fmaf(x.y, y.y, v); v = fmaf(x.z, y.z, v); v = fmaf(x.w, y.w, v);
+            }
+          }
+          flag = v > min_cossim;
+        }
       }
     }
     int off, total;
@@ -214,11 +231,17 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
 // column arg-max by cross-lane reduction in the epilogue -- same results, but the epilogue then out-weighs the saved GEMM
 // (64 x 4096 x 4096: 0.75 ms vs 0.68 ms per call, tools/mnn_ab.py), so it is kept selectable, not default;
 // 3 = implementation 1 on CTA pairs (tcgen05 cta_group::2, M = 256 across two SMs, half the B tile per SM)
-static int g_mnn_impl = 1;
+// 4 = filter + exact re-score (mnn_fast.cu): one fp16 pass per direction, the three-term kernel only on the rows whose top-1 /
+// top-2 gap is within the rounding bound -- same results as 1 at about a third of the tensor work (default)
+static int g_mnn_impl = 4;
+size_t mnn_fast_workspace_bytes(int batch, int n1_max, int n2_max);
+int launch_mnn_fast(const float* f1, const int* n1, int n1_max, int64_t stride1, const float* f2, const int* n2, int n2_max,
+                    int64_t stride2, int batch, void* d_ws, size_t ws_bytes, unsigned long long** best12,
+                    unsigned long long** best21, float** inv_s2, cudaStream_t st, float abs_bound, int sm_count);
 
 }  // namespace xf
 
-extern "C" void xfeat_set_mnn_impl(int impl) { xf::g_mnn_impl = impl < 0 ? 0 : (impl > 3 ? 3 : impl); }
+extern "C" void xfeat_set_mnn_impl(int impl) { xf::g_mnn_impl = impl < 0 ? 0 : (impl > 4 ? 4 : impl); }
 extern "C" int xfeat_get_mnn_impl(void) { return xf::g_mnn_impl; }
 
 extern "C" size_t xfeat_mnn_workspace_bytes(int batch, int n1_max, int n2_max) {
@@ -226,7 +249,8 @@ extern "C" size_t xfeat_mnn_workspace_bytes(int batch, int n1_max, int n2_max) {
   xf::MnnWs ws;
   xf::carve_mnn(bump, batch, n1_max, n2_max, ws);
   const size_t a = bump.used(), b = xf::mnn_tc_workspace_bytes(batch, n1_max, n2_max);
-  return a > b ? a : b;
+  const size_t c = xf::mnn_fast_workspace_bytes(batch, n1_max, n2_max);
+  return (a > b ? a : b) > c ? (a > b ? a : b) : c;
 }
 
 extern "C" int xfeat_mnn_match(const float* d_f1, const int32_t* d_n1, int n1_max, int64_t stride1, const float* d_f2,
@@ -247,6 +271,20 @@ extern "C" int xfeat_mnn_match_bounded(const float* d_f1, const int32_t* d_n1, i
              "mnn_match: descriptors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (!(abs_bound > 0.f) || !isfinite(abs_bound)) abs_bound = 0.f;   // no usable bound: measure max |x| on the device
+  if (xf::g_mnn_impl == 4) {
+    unsigned long long *b12 = nullptr, *b21 = nullptr;
+    float* inv_s2 = nullptr;
+    int dev = 0, sms = 148;
+    XF_CUDA(cudaGetDevice(&dev));
+    XF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int rc = xf::launch_mnn_fast(d_f1, d_n1, n1_max, stride1, d_f2, d_n2, n2_max, stride2, batch, d_ws, ws_bytes, &b12, &b21,
+                                 &inv_s2, st, abs_bound, sms);
+    if (rc) return rc;
+    xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(b12, b21, d_n1, d_n2, n1_max, n2_max, min_cossim, inv_s2, (long long*)d_idx0,
+                                                    (long long*)d_idx1, d_n_matches, d_f1, stride1, d_f2, stride2);
+    XF_LAUNCH_CHECK();
+    return XF_OK;
+  }
   if (xf::g_mnn_impl >= 1) {
     unsigned long long *b12 = nullptr, *b21 = nullptr;
     float* inv_s2 = nullptr;

@@ -85,20 +85,29 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ f,
 struct TcMaps {
   CUtensorMap m1, m2;
 };
+// operand arrays per scan direction: direction d multiplies rows of a<d> (the scanned rows) with rows of b<d> (the columns).
+// Full scan: a0 = b1 = set 1, b0 = a1 = set 2.  Re-scoring pass of mnn_fast.cu: a<d> = compact lists of ambiguous rows.
+struct TcMaps4 {
+  CUtensorMap a0, b0, a1, b1;
+};
 
-__global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_constant__ TcMaps maps,
+// rows_cnt (optional): [pair][dir] number of rows of the A array to scan (the compact lists of mnn_fast.cu) instead of the
+// set size; row_map (optional): [pair][dir][n_pad] output row of compact row r.
+__global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_constant__ TcMaps4 maps,
                                                                const int* __restrict__ n1p, int n1_max,
                                                                const int* __restrict__ n2p, int n2_max, int n_pad,
                                                                unsigned long long* __restrict__ best12,
-                                                               unsigned long long* __restrict__ best21) {
+                                                               unsigned long long* __restrict__ best21,
+                                                               const int* __restrict__ rows_cnt,
+                                                               const int* __restrict__ row_map) {
   const int pair = blockIdx.y, dir = blockIdx.z;
   const int n1 = n1p ? min(n1p[pair], n1_max) : n1_max;
   const int n2 = n2p ? min(n2p[pair], n2_max) : n2_max;
-  const int n_rows = dir ? n2 : n1, n_cols = dir ? n1 : n2;
+  const int n_rows = rows_cnt ? min(rows_cnt[pair * 2 + dir], n_pad) : (dir ? n2 : n1), n_cols = dir ? n1 : n2;
   const int out_stride = dir ? n2_max : n1_max;
   unsigned long long* out = dir ? best21 : best12;
-  const CUtensorMap* mapA = dir ? &maps.m2 : &maps.m1;
-  const CUtensorMap* mapB = dir ? &maps.m1 : &maps.m2;
+  const CUtensorMap* mapA = dir ? &maps.a1 : &maps.a0;
+  const CUtensorMap* mapB = dir ? &maps.b1 : &maps.b0;
   const int row0 = blockIdx.x * TC_ROWS;
   if (row0 >= n_rows) return;
 
@@ -261,7 +270,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
         const unsigned long long o = sMerge[slab * 128 + q * 32 + lane];
         const unsigned long long m = o > pk[slab] ? o : pk[slab];
         const int row = row0 + slab * 128 + q * 32 + lane;
-        if (row < n_rows) out[(int64_t)pair * out_stride + row] = m;
+        if (row < n_rows) {
+          const int orow = row_map ? __ldg(row_map + (int64_t)(pair * 2 + dir) * n_pad + row) : row;
+          out[(int64_t)pair * out_stride + orow] = m;
+        }
       }
     }
   }
@@ -839,7 +851,34 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
     return XF_OK;
   }
   dim3 grid(n_pad / TC_ROWS, batch, 2);
-  mnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(maps, n1, n1_max, n2, n2_max, n_pad, ws.best12, ws.best21);
+  TcMaps4 m4;
+  m4.a0 = maps.m1; m4.b0 = maps.m2; m4.a1 = maps.m2; m4.b1 = maps.m1;
+  mnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(m4, n1, n1_max, n2, n2_max, n_pad, ws.best12, ws.best21, nullptr, nullptr);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+int launch_absmax(const float* f, const int* np, int n_max, int64_t stride, int batch, unsigned* out, cudaStream_t st) {
+  absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(f, np, n_max, stride, out);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+// The three-term kernel on explicit operand arrays (all (batch * n_pad) x 128 halves): direction d scans the first
+// rows_cnt[pair][d] rows of a<d> against set (d ? 1 : 2) in b<d> and writes row r's result at row_map[pair][d][r].
+int launch_mnn_tc_rows(const __half* a0, const __half* b0, const __half* a1, const __half* b1, const int* n1, int n1_max,
+                       const int* n2, int n2_max, int n_pad, int batch, const int* rows_cnt, const int* row_map,
+                       unsigned long long* best12, unsigned long long* best21, cudaStream_t st) {
+  XF_REQUIRE(n_pad % (2 * TC_ROWS) == 0, "mnn_tc_rows: n_pad must be a multiple of %d", 2 * TC_ROWS);
+  TcMaps4 m4;
+  int rc;
+  if ((rc = make_map(&m4.a0, a0, (uint64_t)batch * n_pad))) return rc;
+  if ((rc = make_map(&m4.b0, b0, (uint64_t)batch * n_pad))) return rc;
+  if ((rc = make_map(&m4.a1, a1, (uint64_t)batch * n_pad))) return rc;
+  if ((rc = make_map(&m4.b1, b1, (uint64_t)batch * n_pad))) return rc;
+  XF_DYN_SMEM(mnn_tc_kernel, TC_SMEM);
+  dim3 grid(n_pad / TC_ROWS, batch, 2);
+  mnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(m4, n1, n1_max, n2, n2_max, n_pad, best12, best21, rows_cnt, row_map);
   XF_LAUNCH_CHECK();
   return XF_OK;
 }

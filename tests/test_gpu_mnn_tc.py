@@ -67,7 +67,7 @@ def run(xf, f1, f2, thr):
     return i0.cpu().numpy(), i1.cpu().numpy()
 
 
-TC_IMPLS = [1, 2, 3]   # 1: one GEMM per direction, 2: single pass (row + column arg-max from one accumulator tile), 3: 1 on CTA pairs
+TC_IMPLS = [4, 1, 2, 3]   # 4: filter + exact re-score (default), 1: one 3-term GEMM per direction, 2: single GEMM (row + column arg-max), 3: 1 on CTA pairs
 
 
 @pytest.mark.parametrize("impl", TC_IMPLS)
@@ -160,7 +160,7 @@ def test_tc_full_size_identity(xf, impl):
     assert torch.equal(idx0, idx1) and torch.equal(idx0[3], torch.arange(4096, device="cuda"))
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2, 3])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4])
 def test_exact_ties_first_index(xf, impl):
     """Duplicate descriptors give bit-equal similarities: torch's first-index rule decides (xfeat.py:333-339).  Rows 3/700
     of set 1 and rows 10/450 of set 2 are duplicated; values are small integers / 8 so every product and sum is exact in
@@ -198,3 +198,28 @@ def test_bounded_scale_matches_measured_scale(xf, impl):
         for got, c in ((a, ca), (b, cb)):
             check_modulo_ties(f1[i, :n1[i]], f2[i, :n2[i]], (got[0][i, :c[i]].cpu().numpy(), got[1][i, :c[i]].cpu().numpy()),
                               (w0.numpy(), w1.numpy()))
+
+
+def test_fast_equals_three_term_kernel(xf, assets_vga):
+    """Implementation 4 (filter + exact re-score) against implementation 1 (three-term GEMM everywhere): IDENTICAL index lists,
+    on unit-norm, unnormalised (star path) and near-duplicate (many ambiguous rows) descriptor sets, ragged counts included."""
+    g = torch.Generator().manual_seed(123)
+    cases = []
+    f1 = F.normalize(torch.randn(6, 1100, 64, generator=g), dim=-1)
+    f2 = F.normalize(torch.randn(6, 1100, 64, generator=g), dim=-1)
+    cases.append((f1, f2, [1100, 1000, 513, 512, 3, 1100], [1100, 257, 1100, 640, 1100, 1]))
+    cases.append((torch.randn(3, 900, 64, generator=g) * 13.0, torch.randn(3, 900, 64, generator=g) * 9.0, None, None))
+    base = F.normalize(torch.randn(1, 700, 64, generator=g), dim=-1)
+    near = F.normalize(base + 1e-4 * torch.randn(1, 700, 64, generator=g), dim=-1)       # every row has a runner-up within ~1e-4
+    cases.append((torch.cat([base, near], 1), torch.cat([near, base], 1), None, None))
+    for f1, f2, n1, n2 in cases:
+        B, N = f1.shape[0], f1.shape[1]
+        n1d = None if n1 is None else torch.tensor(n1, dtype=torch.int32).cuda()
+        n2d = None if n2 is None else torch.tensor(n2, dtype=torch.int32).cuda()
+        res = {}
+        for impl in (1, 4):
+            with mnn_impl(xf, impl):
+                res[impl] = xf._mnn_device(f1.cuda(), n1d, N, N * 64, f2.cuda(), n2d, N, N * 64, B, -1)
+        assert torch.equal(res[1][2], res[4][2])
+        for b, c in enumerate(res[1][2].tolist()):
+            assert torch.equal(res[1][0][b, :c], res[4][0][b, :c]) and torch.equal(res[1][1][b, :c], res[4][1][b, :c])
