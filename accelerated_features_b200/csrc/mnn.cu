@@ -231,9 +231,13 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
 // column arg-max by cross-lane reduction in the epilogue -- same results, but the epilogue then out-weighs the saved GEMM
 // (64 x 4096 x 4096: 0.75 ms vs 0.68 ms per call, tools/mnn_ab.py), so it is kept selectable, not default;
 // 3 = implementation 1 on CTA pairs (tcgen05 cta_group::2, M = 256 across two SMs, half the B tile per SM)
-// 4 = filter + exact re-score (mnn_fast.cu): one fp16 pass per direction, the three-term kernel only on the rows whose top-1 /
-// top-2 gap is within the rounding bound -- same results as 1 at about a third of the tensor work (default)
-static int g_mnn_impl = 4;
+// 4 = filter + exact re-score (mnn_fast.cu): one fp16 pass per direction tracking top-1 / top-2, the three-term kernel only on
+// the rows whose gap is within the rounding bound -- same results as 1.  Measured (profiles/r02/mnn_probe.json, 64 x 4096^2):
+// the filter pass is bound by the ALU pipe (FMNMX at 16 lanes/clk: 370 us against 115 us of tensor time), and the descriptors of
+// the bench images (strong common mode, median top-1/top-2 gap 1.6e-3 against a bound of 1.1e-3) send 40 % of the rows to the
+// exact kernel: 0.57 ms vs 0.61 ms on well separated descriptors, 0.80 ms vs 0.61 ms on the bench workload.  Selectable, not
+// default.
+static int g_mnn_impl = 1;
 size_t mnn_fast_workspace_bytes(int batch, int n1_max, int n2_max);
 int launch_mnn_fast(const float* f1, const int* n1, int n1_max, int64_t stride1, const float* f2, const int* n2, int n2_max,
                     int64_t stride2, int batch, void* d_ws, size_t ws_bytes, unsigned long long** best12,

@@ -1,4 +1,4 @@
-// Mutual-NN scan, "filter + exact re-score" formulation (default, xfeat_set_mnn_impl(4)).
+// Mutual-NN scan, "filter + exact re-score" formulation (xfeat_set_mnn_impl(4); see mnn.cu for why it is not the default).
 //
 // mnn_tc_kernel (mnn_tc.cu) computes every similarity in fp32-equivalent precision: three fp16 GEMM passes per direction,
 // 6x the MACs of one similarity matrix.  Almost none of that precision decides anything: a row's arg-max only needs it when
@@ -14,11 +14,12 @@
 //
 // Pass-1 kernel: persistent CTAs (one per SM) over work items (pair, direction, 256-row block); warp 0 = TMA producer (A
 // slabs double buffered across items, 6-stage ring of 128-column B tiles, hi boxes only), warp 1 = MMA issuer
-// (2 slabs x 4 UMMA 128x128x16 per tile, accumulators double buffered in TMEM), warps 2-9 = epilogue: warp -> (TMEM lane
-// quarter, slab), one thread per row.  The epilogue is the bound (a 128x128x64 tile is 256 tensor cycles), so it is
-// branch-light: per 32-column chunk a 3-input max tree over four 8-column groups, a top-2 merge of the group maxima, and --
-// only when some lane's running maximum improves -- a predicated save of the winning group's eight values; the column inside
-// the group and the in-group runner-up are resolved once per row at the end of the item.
+// (2 slabs x 4 UMMA 128x128x16 per tile, accumulators double buffered in TMEM), warps 2-17 = epilogue: warp -> (TMEM lane
+// quarter, slab, 64-column half), one thread per row and half.  The epilogue is the bound (a 128x128x64 tile is 256 tensor
+// cycles) and a dependent chain per row, so it runs 4 warps per scheduler and is branch-light: per 16-column chunk a 3-input
+// max tree over two 8-column groups, a top-2 merge, and -- only when some lane's running maximum improves -- a predicated
+// save of the winning group's eight values; the column inside the group and the in-group runner-up are resolved once per
+// row at the end of the item, after the two column halves have been merged through shared memory.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -28,8 +29,8 @@ namespace xf {
 
 constexpr int MF_ROWS = 256, MF_BN = 128, MF_KP = 128, MF_BOX = 128 * 128;   // hi box: 128 rows x 64 halves
 constexpr int MF_NSB = 6;                                                      // B tile ring depth
-constexpr int MF_THREADS = 320;
-constexpr size_t MF_SMEM = 1024 + (size_t)(4 + MF_NSB) * MF_BOX + 512;
+constexpr int MF_EPI_WARPS = 16, MF_THREADS = 64 + 32 * MF_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
+constexpr size_t MF_SMEM = 1024 + (size_t)(4 + MF_NSB) * MF_BOX + 512 + 2 * 4 * 256 * sizeof(float);
 
 __device__ __forceinline__ float max3f(float a, float b, float c) {
   float r;
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(256) split_norm_kernel(const float* __restrict
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int pair = blockIdx.y;
-  if (wid >= n_pad) return;
+  // grid.x * 8 warps == n_pad exactly (n_pad is a multiple of 512): no warp leaves before the block barrier below
   const int n = np ? min(np[pair], n_max) : n_max;
   const float mx = abs_bound > 0.f ? abs_bound : __uint_as_float(*absmax);
   int e = 0;
@@ -75,14 +76,24 @@ __global__ void __launch_bounds__(256) split_norm_kernel(const float* __restrict
     sh += __shfl_xor_sync(0xffffffffu, sh, k);
     sl += __shfl_xor_sync(0xffffffffu, sl, k);
   }
+  __shared__ float s_nh[8], s_nl[8];
+  float nh = 0.f, nl = 0.f;
   if (lane == 0) {
     // round the norms UP a little: they bound an error, sqrt/add rounding must not shrink them
-    const float nh = sqrtf(sh) * 1.0001f, nl = sqrtf(sl) * 1.0001f;
+    nh = sqrtf(sh) * 1.0001f;
+    nl = sqrtf(sl) * 1.0001f;
     norms[(int64_t)pair * n_pad + wid] = make_float2(nh, nl);
-    if (wid < n) {
-      atomicMax(&maxn[pair * 2 + 0], __float_as_uint(nh));
-      atomicMax(&maxn[pair * 2 + 1], __float_as_uint(nl));
-    }
+    s_nh[threadIdx.x >> 5] = (wid < n) ? nh : 0.f;
+    s_nl[threadIdx.x >> 5] = (wid < n) ? nl : 0.f;
+  }
+  __syncthreads();     // every warp of the block reaches this point (rows past n_pad returned above only in the last block: see launch)
+  if (threadIdx.x == 0) {
+    float mh = 0.f, ml = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mh = fmaxf(mh, s_nh[i]); ml = fmaxf(ml, s_nl[i]); }
+    // one atomic per block, and only when it can raise the maximum (4k warps hammering two words per pair cost 300 us)
+    if (__float_as_uint(mh) > *reinterpret_cast<volatile unsigned*>(&maxn[pair * 2 + 0])) atomicMax(&maxn[pair * 2 + 0], __float_as_uint(mh));
+    if (__float_as_uint(ml) > *reinterpret_cast<volatile unsigned*>(&maxn[pair * 2 + 1])) atomicMax(&maxn[pair * 2 + 1], __float_as_uint(ml));
   }
 }
 
@@ -99,6 +110,49 @@ struct MfParams {
   __half *amb_rows0, *amb_rows1;      // compact operand rows per direction: (batch * n_pad) x 128 halves
 };
 
+// per-row running state of the filter pass
+struct MfRow {
+  float best, m2;     // maximum so far; largest value seen OUTSIDE the 8-column group that holds the maximum
+  float sin;          // runner-up INSIDE that group (== best when the maximum occurs twice in it)
+  int col;            // column of the maximum (first one inside its group)
+};
+
+// one 16-column chunk (two 8-column groups) of one row
+__device__ __forceinline__ void mf_process16(uint32_t (&r)[16], int cb, int n_cols, MfRow& st) {
+  if (cb + 16 > n_cols) {       // chunk straddles or lies past the last valid column (last tile only; warp-uniform)
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (cb + j >= n_cols) r[j] = 0xff800000u;   // -inf
+  }
+  float g[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    g[k] = max3f(max3f(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1]), __uint_as_float(r[8 * k + 2])),
+                 max3f(__uint_as_float(r[8 * k + 3]), __uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5])),
+                 fmaxf(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7])));
+  const float top = fmaxf(g[0], g[1]), sec = fminf(g[0], g[1]);
+  st.m2 = max3f(st.m2, sec, fminf(st.best, top));   // the old maximum (and its group) is "outside" once a new group takes over
+  const bool improve = top > st.best;               // strict: an equal value leaves m2 == best, i.e. an ambiguous row
+  if (__any_sync(0xffffffffu, improve)) {           // rare per lane (~ln N times per row), branch-free inside
+    const bool p0 = (g[0] == top);
+    float w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = p0 ? __uint_as_float(r[j]) : __uint_as_float(r[8 + j]);
+    int jj = 7, cnt = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      const bool eq = (w[j] == top);
+      jj = eq ? j : jj;
+      cnt += eq ? 1 : 0;
+      w[j] = eq ? -INFINITY : w[j];
+    }
+    const float others = max3f(max3f(w[0], w[1], w[2]), max3f(w[3], w[4], w[5]), fmaxf(w[6], w[7]));
+    st.sin = improve ? (cnt > 1 ? top : others) : st.sin;
+    st.col = improve ? cb + (p0 ? 0 : 8) + jj : st.col;
+  }
+  st.best = fmaxf(st.best, top);
+}
+
 __global__ void __launch_bounds__(MF_THREADS, 1) mnn_fast_kernel(const __grid_constant__ MfParams P) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -112,6 +166,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mnn_fast_kernel(const __grid_co
   uint64_t* acc_full = b_empty + MF_NSB;          // [2]
   uint64_t* acc_empty = acc_full + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sMerge = reinterpret_cast<float*>(base + (4 + MF_NSB) * MF_BOX + 512);   // [item parity 2][field 4][256 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int RB = P.n_pad / MF_ROWS;
@@ -124,7 +179,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mnn_fast_kernel(const __grid_co
       tc::mbar_init(&a_full[i], 1);
       tc::mbar_init(&a_empty[i], 1);
       tc::mbar_init(&acc_full[i], 1);
-      tc::mbar_init(&acc_empty[i], 8);
+      tc::mbar_init(&acc_empty[i], MF_EPI_WARPS);
     }
     for (int i = 0; i < MF_NSB; ++i) {
       tc::mbar_init(&b_full[i], 1);
@@ -214,118 +269,97 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mnn_fast_kernel(const __grid_co
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue ----------------
-    const int q = warp & 3, slab = (warp - 2) >> 2;
-    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + slab * 128;
-    uint32_t tt = 0;
+    // ---------------- epilogue: 16 warps = (TMEM lane quarter q) x (slab) x (64-column half hc) ----------------
+    // The reduction is a dependent chain per row, so thread-level parallelism (4 warps per scheduler) is what fills the
+    // issue slots; each warp drains 4 x 16 columns of one slab per tile.
+    const int e = warp - 2;
+    const int q = warp & 3, slab = (e >> 2) & 1, hc = e >> 3;
+    const int rl = slab * 128 + q * 32 + lane;                 // row of the item owned by this thread
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + slab * 128 + hc * 64;
+    uint32_t tt = 0, icount = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       int pair, dir, row0, n_rows, n_cols;
       if (!decode(item, pair, dir, row0, n_rows, n_cols)) continue;
       const int T = (n_cols + MF_BN - 1) / MF_BN;
-      const int row = row0 + slab * 128 + q * 32 + lane;
-      float best = -INFINITY, m2 = -INFINITY;
-      int loc = 0;
-      float sv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sv[j] = -INFINITY;
-
-      auto process = [&](uint32_t (&r)[32], int cb) {
-        if (cb + 32 > n_cols) {       // chunk straddles or lies past the last valid column (last tile only)
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (cb + j >= n_cols) r[j] = 0xff800000u;   // -inf
-        }
-        float g[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          g[k] = max3f(max3f(__uint_as_float(r[8 * k]), __uint_as_float(r[8 * k + 1]), __uint_as_float(r[8 * k + 2])),
-                       max3f(__uint_as_float(r[8 * k + 3]), __uint_as_float(r[8 * k + 4]), __uint_as_float(r[8 * k + 5])),
-                       fmaxf(__uint_as_float(r[8 * k + 6]), __uint_as_float(r[8 * k + 7])));
-        const float a = fmaxf(g[0], g[1]), b = fminf(g[0], g[1]), c = fmaxf(g[2], g[3]), d = fminf(g[2], g[3]);
-        const float top = fmaxf(a, c), sec = max3f(fminf(a, c), b, d);
-        m2 = max3f(m2, sec, fminf(best, top));       // runner-up over everything seen so far, outside the best GROUP
-        const bool improve = top > best;             // strict: an equal value leaves m2 == best, i.e. an ambiguous row
-        if (__any_sync(0xffffffffu, improve)) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const bool pk = improve && (g[k] == top);
-            if (__any_sync(0xffffffffu, pk)) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) sv[j] = pk ? __uint_as_float(r[8 * k + j]) : sv[j];
-              loc = pk ? cb + 8 * k : loc;
-            }
-          }
-        }
-        best = fmaxf(best, top);
-      };
+      const int row = row0 + rl;
+      MfRow st;
+      st.best = -INFINITY; st.m2 = -INFINITY; st.sin = -INFINITY; st.col = 0;
 
       for (int t = 0; t < T; ++t, ++tt) {
         const int as = tt & 1;
         tc::mbar_wait(&acc_full[as], (tt >> 1) & 1);
         tc::tc_fence_after();
         const uint32_t tb = lane_addr + as * 256;
-        const int cb = t * MF_BN;
-        uint32_t ra[32], rb[32];
+        const int cb = t * MF_BN + hc * 64;
+        // all four loads first, ONE wait, and the TMEM buffer goes straight back to the MMA warp: the accumulator double buffer
+        // then hides the whole reduction (holding the buffer across the reduction made the tile time MMA + epilogue / 2)
+        uint32_t ra[16], rb[16], rc[16], rd[16];
         __syncwarp();
-        tc::tmem_ld_32x32(tb, ra);
-        tc::tmem_ld_wait();
-        __syncwarp();
-        tc::tmem_ld_32x32(tb + 32, rb);
-        process(ra, cb);
-        tc::tmem_ld_wait();
-        __syncwarp();
-        tc::tmem_ld_32x32(tb + 64, ra);
-        process(rb, cb + 32);
-        tc::tmem_ld_wait();
-        __syncwarp();
-        tc::tmem_ld_32x32(tb + 96, rb);
-        process(ra, cb + 64);
+        tc::tmem_ld_32x16(tb, ra);
+        tc::tmem_ld_32x16(tb + 16, rb);
+        tc::tmem_ld_32x16(tb + 32, rc);
+        tc::tmem_ld_32x16(tb + 48, rd);
         tc::tmem_ld_wait();
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&acc_empty[as]);   // all TMEM reads of this buffer (by this warp) are done
-        process(rb, cb + 96);
+        mf_process16(ra, cb, n_cols, st);
+        mf_process16(rb, cb + 16, n_cols, st);
+        mf_process16(rc, cb + 32, n_cols, st);
+        mf_process16(rd, cb + 48, n_cols, st);
       }
 
-      // ---- end of the item: resolve the column inside the best group, the runner-up, and the ambiguity test ----
-      int j0 = 7;
-#pragma unroll
-      for (int j = 6; j >= 0; --j)
-        if (sv[j] == best) j0 = j;
-      float sec_in = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sec_in = fmaxf(sec_in, (j == j0) ? -INFINITY : sv[j]);
-      const float second = fmaxf(m2, sec_in);
-      const bool live = row < n_rows;
-      bool amb = false;
-      if (live) {
-        const float2 nr = __ldg((dir ? P.norms2 : P.norms1) + (int64_t)pair * P.n_pad + row);
-        const unsigned* mo = (dir ? P.maxn1 : P.maxn2) + pair * 2;            // the OTHER set's maxima
-        const float Hmax = __uint_as_float(__ldg(mo)), Lmax = __uint_as_float(__ldg(mo + 1));
-        // |S~ - S| <= ||hi_i|| Lmax + ||lo_i|| Hmax for every column; both the best and a competitor may be off by that much;
-        // 2^-14 ||hi_i|| Hmax covers the fp32 accumulation-order difference between the one-term and the three-term sums.
-        const float tau = 2.1f * (nr.x * Lmax + nr.y * Hmax) + 6.2e-5f * nr.x * Hmax;
-        amb = !(best - second > tau);                                           // also true for NaN / -inf oddities
-        unsigned long long* out = dir ? P.best21 : P.best12;
-        out[(int64_t)pair * (dir ? P.n2_max : P.n1_max) + row] = pack_vi(best, (uint32_t)(loc + j0));
+      // ---- end of the item: merge the two column halves of every row through shared memory (double buffered by item) ----
+      float* mg = sMerge + (icount & 1) * (4 * 256);
+      ++icount;
+      if (hc == 1) {
+        mg[0 * 256 + rl] = st.best;
+        mg[1 * 256 + rl] = st.m2;
+        mg[2 * 256 + rl] = st.sin;
+        mg[3 * 256 + rl] = __int_as_float(st.col);
       }
-      // ambiguous rows: append (row index + split operand row) to the compact list of this (pair, direction)
-      unsigned mask = __ballot_sync(0xffffffffu, amb);
-      if (mask) {
-        const int pd = pair * 2 + dir;
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(P.amb_cnt + pd, __popc(mask));
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        const __half* src_set = dir ? P.f2s : P.f1s;
-        __half* dst_set = dir ? P.amb_rows1 : P.amb_rows0;
-        while (mask) {
-          const int l = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int src_row = __shfl_sync(0xffffffffu, row, l);
-          const uint2 v = __ldg(reinterpret_cast<const uint2*>(src_set + ((int64_t)pair * P.n_pad + src_row) * MF_KP) + lane);
-          reinterpret_cast<uint2*>(dst_set + ((int64_t)pair * P.n_pad + slot) * MF_KP)[lane] = v;
-          if (lane == 0) P.amb_idx[(int64_t)pd * P.n_pad + slot] = src_row;
-          ++slot;
+      asm volatile("bar.sync 1, 512;" ::: "memory");     // epilogue warps only
+      if (hc == 0) {
+        const float ob = mg[0 * 256 + rl], om2 = mg[1 * 256 + rl];
+        const bool other = ob > st.best;                  // a tie keeps the lower columns; the row is ambiguous anyway
+        st.m2 = max3f(st.m2, om2, fminf(st.best, ob));
+        if (other) {
+          st.best = ob;
+          st.sin = mg[2 * 256 + rl];
+          st.col = __float_as_int(mg[3 * 256 + rl]);
+        }
+        const float second = fmaxf(st.m2, st.sin);
+        const bool live = row < n_rows;
+        bool amb = false;
+        if (live) {
+          const float2 nr = __ldg((dir ? P.norms2 : P.norms1) + (int64_t)pair * P.n_pad + row);
+          const unsigned* mo = (dir ? P.maxn1 : P.maxn2) + pair * 2;            // the OTHER set's maxima
+          const float Hmax = __uint_as_float(__ldg(mo)), Lmax = __uint_as_float(__ldg(mo + 1));
+          // |S~ - S| <= ||hi_i|| Lmax + ||lo_i|| Hmax for every column; both the best and a competitor may be off by that much;
+          // 2^-14 ||hi_i|| Hmax covers the fp32 accumulation-order difference between the one-term and the three-term sums.
+          const float tau = 2.1f * (nr.x * Lmax + nr.y * Hmax) + 6.2e-5f * nr.x * Hmax;
+          amb = !(st.best - second > tau);                                       // also true for NaN / -inf oddities
+          unsigned long long* out = dir ? P.best21 : P.best12;
+          out[(int64_t)pair * (dir ? P.n2_max : P.n1_max) + row] = pack_vi(st.best, (uint32_t)st.col);
+        }
+        // ambiguous rows: append (row index + split operand row) to the compact list of this (pair, direction)
+        unsigned mask = __ballot_sync(0xffffffffu, amb);
+        if (mask) {
+          const int pd = pair * 2 + dir;
+          int slot = 0;
+          if (lane == 0) slot = atomicAdd(P.amb_cnt + pd, __popc(mask));
+          slot = __shfl_sync(0xffffffffu, slot, 0);
+          const __half* src_set = dir ? P.f2s : P.f1s;
+          __half* dst_set = dir ? P.amb_rows1 : P.amb_rows0;
+          while (mask) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int src_row = __shfl_sync(0xffffffffu, row, l);
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(src_set + ((int64_t)pair * P.n_pad + src_row) * MF_KP) + lane);
+            reinterpret_cast<uint2*>(dst_set + ((int64_t)pair * P.n_pad + slot) * MF_KP)[lane] = v;
+            if (lane == 0) P.amb_idx[(int64_t)pd * P.n_pad + slot] = src_row;
+            ++slot;
+          }
         }
       }
     }

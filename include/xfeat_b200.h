@@ -125,8 +125,8 @@ XF_API int xfeat_detect_dense(xfeat_ctx* ctx, const float* d_feats, const float*
                        void* stream);
 
 /* Implementation switch of xfeat_mnn_match (process-wide): 0 = fp32 CUDA-core kernel; 1 = tcgen05 tensor-core kernel
- * (split-fp16 operands, fp32 accumulation in TMEM, one three-term GEMM per direction); 2 = tcgen05, single GEMM with the
- * column arg-max reduced in the epilogue; 3 = implementation 1 on CTA pairs (tcgen05 cta_group::2); 4 (default) = filter +
+ * (split-fp16 operands, fp32 accumulation in TMEM, one three-term GEMM per direction; default); 2 = tcgen05, single GEMM with the
+ * column arg-max reduced in the epilogue; 3 = implementation 1 on CTA pairs (tcgen05 cta_group::2); 4 = filter +
  * exact re-score: one fp16 pass per direction tracking top-1 / top-2, then implementation 1's kernel only on the rows whose
  * gap is within the rounding bound of the dropped split terms.  All honour the same tie rule; 1-4 return identical results.
  * Values outside 0..4 are clamped. */

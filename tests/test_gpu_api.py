@@ -31,7 +31,7 @@ def test_preprocess_tensor(xf, assets_vga):
     want, rh, rw = orc.preprocess_tensor(crop)
     got, grh, grw = xf.preprocess_tensor(crop)
     assert (grh, grw) == (rh, rw) and got.shape == want.shape and got.dtype == torch.float32
-    assert (got.cpu() - want).abs().max().item() < 1e-4                              # uint8 scale values, no /255 here (xfeat.py:221-233)
+    assert (got.cpu() - want).abs().max().item() < 2e-3                              # values up to 255 (no /255 here, xfeat.py:221-233): 1e-5 relative
     x = torch.rand(2, 3, 64, 96)
     got, grh, grw = xf.preprocess_tensor(x)                                          # identity resize still runs (xfeat.py:239)
     assert grh == 1.0 and grw == 1.0 and (got.cpu() - x).abs().max().item() < 1e-6
