@@ -389,8 +389,8 @@ class XFeat(torch.nn.Module):
             self.done = [torch.cuda.Event(), torch.cuda.Event()]
 
     def pinned_like(self, shape, dtype=torch.uint8) -> torch.Tensor:
-        """A page-locked host tensor: fill it (e.g. through `.numpy()`) and hand it to match_xfeat_stream / match_xfeat_batch
-        to skip the staging copy that pageable memory needs."""
+        """A page-locked host tensor.  Fill it and hand it (a (B,C,H,W) tensor) -- or its `.numpy()` view for (B,H,W,C) uint8
+        camera frames -- to match_xfeat_stream / match_xfeat_batch: pinned memory skips the staging copy pageable memory needs."""
         return torch.empty(shape, dtype=dtype, pin_memory=True)
 
     def _host_batch(self, x) -> Tuple[torch.Tensor, bool, bool]:

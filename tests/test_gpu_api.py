@@ -150,7 +150,7 @@ def test_stream_equals_batch_and_single(xf, assets_vga):
     single = [xf.match_xfeat(a, b, top_k=1500) for a, b in zip(b1, b2)]
     pinned = xf.pinned_like(b1.shape)
     pinned.numpy()[:] = b1
-    batches = [(b1, b2), (pinned, torch.from_numpy(b2)), (b1[:2], b2[:2]), (b1, b2)]     # pageable, pinned, other shape
+    batches = [(b1, b2), (pinned.numpy(), b2), (b1[:2], b2[:2]), (b1, b2)]     # pageable, pinned (numpy view), other shape
     outs = list(xf.match_xfeat_stream(batches, top_k=1500))
     assert len(outs) == 4 and [len(o) for o in outs] == [4, 4, 2, 4]
     for o in outs:
