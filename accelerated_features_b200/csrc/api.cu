@@ -102,10 +102,13 @@ extern "C" int xfeat_create(xfeat_ctx** out, int device, const float* packed_hos
     return XF_E_CUDA;
   }
   c->d_tcw = nullptr;
-  const int rc = xf::conv_tc_prepare(c);
+  c->d_mlpw = nullptr;
+  int rc = xf::conv_tc_prepare(c);
+  if (rc == XF_OK) rc = xf::mlp_tc_prepare(c);
   if (rc != XF_OK) {
     cudaFree(c->d_weights);
     if (c->d_tcw) cudaFree(c->d_tcw);
+    if (c->d_mlpw) cudaFree(c->d_mlpw);
     free(c->h_weights);
     delete c;
     return rc;
@@ -122,6 +125,7 @@ extern "C" void xfeat_destroy(xfeat_ctx* ctx) {
   xf::DeviceGuard guard(ctx->device);
   if (ctx->d_weights) cudaFree(ctx->d_weights);
   if (ctx->d_tcw) cudaFree(ctx->d_tcw);
+  if (ctx->d_mlpw) cudaFree(ctx->d_mlpw);
   free(ctx->h_weights);
   delete ctx;
 }

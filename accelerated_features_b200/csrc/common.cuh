@@ -147,6 +147,10 @@ struct xfeat_ctx {
   void* d_tcw;
   size_t tc_off[xf::L_COUNT];
   float tc_inv_wscale[xf::L_COUNT];
+  // fine-matcher MLP on the tensor cores (mlp_tc.cu): split fp16 weights [N][whi(K) | wlo(K)] of the five Linear layers
+  void* d_mlpw;
+  size_t mlp_off[5];
+  float mlp_inv_scale[5];
 };
 
 // ---- stage launchers shared between translation units -------------------------------------------------
@@ -159,6 +163,9 @@ bool conv_tc_eligible(int layer);
 int launch_conv_tc_halo(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int H, int W, __half* out_split,
                         float* out_f32, cudaStream_t st);
 int conv_tc_prepare(xfeat_ctx* ctx);
+int mlp_tc_prepare(xfeat_ctx* ctx);
+int launch_fine_mlp_tc(const xfeat_ctx* ctx, const __half* X_split, int rows_cap, const int* n_live, __half* act_a, __half* act_b,
+                       float* logits, cudaStream_t st);
 int launch_conv_tc(const xfeat_ctx* ctx, int layer, const __half* in_split, int B, int H, int W, __half* out_split,
                    float* out_f32, cudaStream_t st, const float* skip_xn = nullptr);
 int launch_head_chain(const xfeat_ctx* ctx, int mode, const __half* in_split, int B, int Hc, int Wc, float* out, float* logits,

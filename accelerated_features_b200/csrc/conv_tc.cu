@@ -251,31 +251,11 @@ __global__ void __launch_bounds__(CT_THREADS2, 1) conv_tc_kernel(const __grid_co
 #pragma unroll
           for (int c = 0; c < NOUT; ++c) o[c] += fmaf(skipv, sSkip[c], sSkip[NOUT + c]);
         }
-        if (P.out_f32) {
-          float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * P.f32_c + P.f32_co0);
-#pragma unroll
-          for (int c = 0; c < NOUT / 4; ++c)
-            if (4 * c < P.n_real) op[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-        }
+        if (P.out_f32) tc::store_f32_row<NOUT>(P.out_f32 + pix * P.f32_c + P.f32_co0, o, P.n_real);
         if (P.out_split) {
           // [hi(split_c) | lo(split_c)]; this N tile owns channels f32_co0 .. f32_co0+NOUT-1 (padded channels: exact zeros)
-          uint4* hp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * P.split_c) + P.f32_co0);
-          uint4* lp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * P.split_c) + P.split_c + P.f32_co0);
-#pragma unroll
-          for (int c = 0; c < NOUT / 8; ++c) {
-            __half2 h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x0 = o[8 * c + 2 * j], x1 = o[8 * c + 2 * j + 1];
-              h[j] = __floats2half2_rn(x0, x1);
-              const float2 hf = __half22float2(h[j]);
-              l[j] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-            }
-            hp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
-                               *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
-            lp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
-                               *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
-          }
+          __half* hp = P.out_split + pix * (2 * P.split_c) + P.f32_co0;
+          tc::store_split_row<NOUT>(hp, hp + P.split_c, o);
         }
       }
     }
@@ -426,29 +406,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) conv_tc128_kernel(const __grid_
           if (P.relu) { t0 = fmaxf(t0, 0.f); t1 = fmaxf(t1, 0.f); }
           o[c] = t0; o[32 + c] = t1;
         }
-        if (P.out_f32) {
-          float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * P.f32_c + co0);
-#pragma unroll
-          for (int c = 0; c < 16; ++c) op[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-        }
+        if (P.out_f32) tc::store_f32_row<NOUT>(P.out_f32 + pix * P.f32_c + co0, o, NOUT);
         if (P.out_split) {
-          uint4* hp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * P.split_c) + co0);
-          uint4* lp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * P.split_c) + P.split_c + co0);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            __half2 h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x0 = o[8 * c + 2 * j], x1 = o[8 * c + 2 * j + 1];
-              h[j] = __floats2half2_rn(x0, x1);
-              const float2 hf = __half22float2(h[j]);
-              l[j] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-            }
-            hp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
-                               *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
-            lp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
-                               *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
-          }
+          __half* hp = P.out_split + pix * (2 * P.split_c) + co0;
+          tc::store_split_row<NOUT>(hp, hp + P.split_c, o);
         }
       }
     }

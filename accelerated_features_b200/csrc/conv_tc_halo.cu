@@ -240,29 +240,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
           if (P.relu) t0 = fmaxf(t0, 0.f);
           o[c] = t0;
         }
-        if (P.out_f32) {
-          float4* op = reinterpret_cast<float4*>(P.out_f32 + pix * P.f32_c);
-#pragma unroll
-          for (int c = 0; c < NOUT / 4; ++c)
-            if (4 * c < P.n_real) op[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-        }
+        if (P.out_f32) tc::store_f32_row<NOUT>(P.out_f32 + pix * P.f32_c, o, P.n_real);
         if (P.out_split) {
-          uint4* hp = reinterpret_cast<uint4*>(P.out_split + pix * (2 * NOUT));
-#pragma unroll
-          for (int c = 0; c < NOUT / 8; ++c) {
-            __half2 h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x0 = o[8 * c + 2 * j], x1 = o[8 * c + 2 * j + 1];
-              h[j] = __floats2half2_rn(x0, x1);
-              const float2 hf = __half22float2(h[j]);
-              l[j] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-            }
-            hp[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
-                               *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
-            hp[NOUT / 8 + c] = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
-                                          *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
-          }
+          __half* hp = P.out_split + pix * (2 * NOUT);
+          tc::store_split_row<NOUT>(hp, hp + NOUT, o);
         }
       }
     }

@@ -2,6 +2,7 @@
 // of modules/xfeat.py).  Inside detectAndCompute / match_xfeat_star the same arithmetic runs fused in the stage kernels
 // (head_chain_tc.cu, sparse.cu, refine.cu); these entry points exist so that XFeat.get_kpts_heatmap, XFeat.NMS,
 // XFeat.subpix_softmax2d and XFeat.net.fine_matcher are kernels of this library too, not PyTorch ops.
+#include <cuda_fp16.h>
 #include <cub/block/block_scan.cuh>
 
 #include "common.cuh"
@@ -201,6 +202,21 @@ __global__ void __launch_bounds__(256) interpolate_sparse_kernel(const float* __
   out[gid] = o;
 }
 
+// fp32 rows (n, 128) -> split fp16 rows [hi(128) | lo(128)] for the tensor-core MLP; one warp per row
+__global__ void __launch_bounds__(256) split_rows128_kernel(const float* __restrict__ x, int64_t n, __half* __restrict__ out) {
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= n) return;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x + wid * 128) + lane);
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  __half2* o = reinterpret_cast<__half2*>(out + wid * 256);
+  o[2 * lane] = h0;
+  o[2 * lane + 1] = h1;
+  o[64 + 2 * lane] = __floats2half2_rn(v.x - f0.x, v.y - f0.y);
+  o[64 + 2 * lane + 1] = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+}
+
 int launch_fine_mlp(const xfeat_ctx* ctx, const float* X, int rows_cap, const int* n_live, float* actA, float* actB,
                     float* logits, cudaStream_t st);
 
@@ -262,7 +278,8 @@ extern "C" int xfeat_subpix_softmax2d(const float* d_maps, int64_t n, float temp
 }
 
 extern "C" size_t xfeat_fine_matcher_workspace_bytes(int n) {
-  return 2 * xf::align_up((size_t)(n > 0 ? n : 1) * 512 * sizeof(float), 256);
+  const size_t rows = (size_t)(n > 0 ? n : 1);
+  return 2 * xf::align_up(rows * 512 * sizeof(float), 256) + xf::align_up(rows * 256 * sizeof(__half), 256);
 }
 
 extern "C" int xfeat_fine_matcher(xfeat_ctx* ctx, const float* d_x, int n, float* d_out, void* d_ws, size_t ws_bytes,
@@ -273,6 +290,12 @@ extern "C" int xfeat_fine_matcher(xfeat_ctx* ctx, const float* d_x, int n, float
   XF_CUDA(cudaSetDevice(ctx->device));
   float* actA = (float*)d_ws;
   float* actB = (float*)((char*)d_ws + xf::align_up((size_t)n * 512 * sizeof(float), 256));
+  if (xf::g_conv_impl != 0) {
+    __half* xs = (__half*)((char*)d_ws + 2 * xf::align_up((size_t)n * 512 * sizeof(float), 256));
+    xf::split_rows128_kernel<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, n, xs);
+    XF_LAUNCH_CHECK();
+    return xf::launch_fine_mlp_tc(ctx, xs, n, nullptr, (__half*)actA, (__half*)actB, d_out, (cudaStream_t)stream);
+  }
   return xf::launch_fine_mlp(ctx, d_x, n, nullptr, actA, actB, d_out, (cudaStream_t)stream);
 }
 

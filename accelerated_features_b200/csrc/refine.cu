@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) refine_gather_kernel(const float* __restr
                                                             const long long* __restrict__ idx1,
                                                             const int* __restrict__ n_matches,
                                                             const int* __restrict__ offsets, int batch, int n_max,
-                                                            int n1_max, float* __restrict__ X) {
+                                                            int n1_max, float* __restrict__ X, __half* __restrict__ Xs) {
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= (int64_t)batch * n_max) return;
@@ -49,6 +49,16 @@ __global__ void __launch_bounds__(256) refine_gather_kernel(const float* __restr
   const long long a = idx0[wid], b = idx1[wid];
   const float2 u = __ldg(reinterpret_cast<const float2*>(d0 + ((int64_t)pair * n_max + a) * 64) + lane);
   const float2 v = __ldg(reinterpret_cast<const float2*>(d1 + ((int64_t)pair * n1_max + b) * 64) + lane);
+  if (Xs) {   // tensor-core MLP: split fp16 row [hi(128) | lo(128)] (mlp_tc.cu)
+    const __half2 uh = __floats2half2_rn(u.x, u.y), vh = __floats2half2_rn(v.x, v.y);
+    const float2 uf = __half22float2(uh), vf = __half22float2(vh);
+    __half2* o = reinterpret_cast<__half2*>(Xs + row * 256);
+    o[lane] = uh;
+    o[32 + lane] = vh;
+    o[64 + lane] = __floats2half2_rn(u.x - uf.x, u.y - uf.y);
+    o[96 + lane] = __floats2half2_rn(v.x - vf.x, v.y - vf.y);
+    return;
+  }
   reinterpret_cast<float2*>(X + row * 128)[lane] = u;
   reinterpret_cast<float2*>(X + row * 128 + 64)[lane] = v;
 }
@@ -181,14 +191,21 @@ extern "C" int xfeat_refine(xfeat_ctx* ctx, const float* d_desc0, const float* d
   }
   const int64_t cap = (int64_t)batch * n_max;
   const unsigned wblocks = (unsigned)((cap * 32 + 255) / 256);
+  const bool tc = xf::g_conv_impl != 0;   // xfeat_set_conv_impl(0): everything on the fp32 CUDA-core kernels (A/B reference)
   xf::scan_counts_kernel<<<1, 1024, 0, st>>>(d_n_matches, batch, n_max, ws.offsets);
   XF_LAUNCH_CHECK();
   xf::refine_gather_kernel<<<wblocks, 256, 0, st>>>(d_desc0, d_desc1, (const long long*)d_idx0, (const long long*)d_idx1,
-                                                    d_n_matches, ws.offsets, batch, n_max, n1_max, ws.X);
+                                                    d_n_matches, ws.offsets, batch, n_max, n1_max, ws.X,
+                                                    tc ? (__half*)ws.X : nullptr);
   XF_LAUNCH_CHECK();
   const int* n_live = ws.offsets + batch;
   int rc;
-  if ((rc = xf::launch_fine_mlp(ctx, ws.X, (int)cap, n_live, ws.actA, ws.actB, ws.logits, st))) return rc;
+  if (tc) {   // X (cap x 128 floats) holds the split row (cap x 256 halves); actA / actB (cap x 512 floats) hold cap x 1024 halves
+    if ((rc = xf::launch_fine_mlp_tc(ctx, (const __half*)ws.X, (int)cap, n_live, (__half*)ws.actA, (__half*)ws.actB, ws.logits, st)))
+      return rc;
+  } else if ((rc = xf::launch_fine_mlp(ctx, ws.X, (int)cap, n_live, ws.actA, ws.actB, ws.logits, st))) {
+    return rc;
+  }
   xf::refine_finish_kernel<<<wblocks, 256, 0, st>>>(ws.logits, d_kpts0, d_kpts1, d_scales0, (const long long*)d_idx0,
                                                     (const long long*)d_idx1, d_n_matches, ws.offsets, batch, n_max, n1_max,
                                                     fine_conf, ws.tmp, ws.keep);

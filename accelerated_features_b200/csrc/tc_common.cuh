@@ -3,6 +3,7 @@
 // instruction descriptor for kind::f16 / kind::tf32).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -203,6 +204,66 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+
+// ---------------------------------------------------------------- epilogue stores
+// 256-bit global store (sm_100: STG.E.ENL2.256): one full 32-byte sector per thread and instruction.  The conv epilogues write
+// one pixel row per thread, so a warp-wide store touches 32 different rows; with 16-byte pieces every sector is written in two
+// halves by two instructions (LSU-bound: lg_throttle in profiles/r01/ncu_conv_tc_1x1_dual.md), with 32-byte pieces in one.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// N fp32 values -> split fp16 row pieces: hi block at hp, lo block at lp (N halves each), x = hi + lo.  hp / lp 32-byte aligned
+// for N >= 16; N == 8: lp == hp + 8 and the 32-byte row [hi(8) | lo(8)] goes out as one store.
+template <int N>
+__device__ __forceinline__ void store_split_row(__half* hp, __half* lp, const float (&o)[N]) {
+  static_assert(N == 8 || N % 16 == 0, "store_split_row: N");
+  if constexpr (N == 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(o[2 * j] - hf.x, o[2 * j + 1] - hf.y);
+      v[j] = *reinterpret_cast<const uint32_t*>(&h);
+      v[4 + j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    st_global_v8(hp, v);
+  } else {
+#pragma unroll
+    for (int c = 0; c < N / 16; ++c) {
+      uint32_t vh[8], vl[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x0 = o[16 * c + 2 * j], x1 = o[16 * c + 2 * j + 1];
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        vh[j] = *reinterpret_cast<const uint32_t*>(&h);
+        vl[j] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+      st_global_v8(hp + 16 * c, vh);
+      st_global_v8(lp + 16 * c, vl);
+    }
+  }
+}
+// N fp32 values to a 32-byte aligned fp32 row, the first n_real of them (a multiple of 4)
+template <int N>
+__device__ __forceinline__ void store_f32_row(float* op, const float (&o)[N], int n_real) {
+#pragma unroll
+  for (int c = 0; c < N / 8; ++c) {
+    if (8 * c + 8 <= n_real) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(o[8 * c + j]);
+      st_global_v8(op + 8 * c, v);
+    } else if (8 * c < n_real) {
+      reinterpret_cast<float4*>(op + 8 * c)[0] = make_float4(o[8 * c], o[8 * c + 1], o[8 * c + 2], o[8 * c + 3]);
+    }
+  }
+}
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows are 128 B apart inside an 8-row atom
