@@ -2,6 +2,7 @@
 // (heatmap_head.2 + sigmoid, model.py:82-83), keypoint head tail (keypoint_head.3 + softmax(65) + drop dustbin +
 // 8x8 depth-to-space, model.py:91 + xfeat.py:242-247).
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace xf {
 
@@ -147,70 +148,66 @@ __global__ void __launch_bounds__(KPT_WARPS * 32) kpt_softmax_kernel(const float
 
 // Same fusion, but x3 / x4 / x5 arrive as split fp16 [hi(64) | lo(64)] (x = hi + lo) straight from the tensor-core layers, so
 // block3.2 / block4.2 / block5.3 need not write a second, fp32 copy of their output.
-struct F8 {
-  float v[8];
+// 16 channels per thread: 256-bit loads (LDG.E.ENL2.256) of the hi and lo halves, 256-bit stores: half the instructions per byte
+// of the 128-bit version (the kernel is issue-bound on its 18 loads per thread).
+struct F16v {
+  float v[16];
 };
-__device__ __forceinline__ F8 ld_split8(const __half* __restrict__ base, int64_t pix, int c8) {
-  const uint4 h = __ldg(reinterpret_cast<const uint4*>(base + pix * 128 + c8 * 8));
-  const uint4 l = __ldg(reinterpret_cast<const uint4*>(base + pix * 128 + 64 + c8 * 8));
-  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-  F8 r;
+__device__ __forceinline__ void ld_v8_nc(const void* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ F16v ld_split16(const __half* __restrict__ base, int64_t pix, int c16) {
+  uint32_t hw[8], lw[8];
+  ld_v8_nc(base + pix * 128 + c16 * 16, hw);
+  ld_v8_nc(base + pix * 128 + 64 + c16 * 16, lw);
+  F16v r;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[i])), c = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
     r.v[2 * i] = a.x + c.x;
     r.v[2 * i + 1] = a.y + c.y;
   }
   return r;
 }
-// 8 channels per thread: 128-bit loads of the hi and lo halves (the 64-bit-load version ran at 163 us vs 116 us for fp32 inputs)
 __global__ void __launch_bounds__(256) fuse_pyramid_split_kernel(const __half* __restrict__ x3, const __half* __restrict__ x4,
                                                                  const __half* __restrict__ x5, __half* __restrict__ out_split,
-                                                                 int H3, int W3, int H4, int W4, int H5, int W5, int64_t total8) {
+                                                                 int H3, int W3, int H4, int W4, int H5, int W5, int64_t total16) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int c8 = (int)(i & 7);
-  int64_t p = i >> 3;
+  if (i >= total16) return;
+  const int c16 = (int)(i & 3);
+  int64_t p = i >> 2;
   const int x = (int)(p % W3);
   p /= W3;
   const int y = (int)(p % H3);
   const int b = (int)(p / H3);
-  F8 r = ld_split8(x3, i >> 3, c8);
+  F16v r = ld_split16(x3, i >> 2, c16);
   {
     const LinTap ty = lin_tap(y, (float)H4 / (float)H3, H4), tx = lin_tap(x, (float)W4 / (float)W3, W4);
     const int64_t bb = (int64_t)b * H4 * W4;
-    const F8 v00 = ld_split8(x4, bb + (int64_t)ty.i0 * W4 + tx.i0, c8), v01 = ld_split8(x4, bb + (int64_t)ty.i0 * W4 + tx.i1, c8);
-    const F8 v10 = ld_split8(x4, bb + (int64_t)ty.i1 * W4 + tx.i0, c8), v11 = ld_split8(x4, bb + (int64_t)ty.i1 * W4 + tx.i1, c8);
+    const F16v v00 = ld_split16(x4, bb + (int64_t)ty.i0 * W4 + tx.i0, c16), v01 = ld_split16(x4, bb + (int64_t)ty.i0 * W4 + tx.i1, c16);
+    const F16v v10 = ld_split16(x4, bb + (int64_t)ty.i1 * W4 + tx.i0, c16), v11 = ld_split16(x4, bb + (int64_t)ty.i1 * W4 + tx.i1, c16);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r.v[k] += ty.l0 * (tx.l0 * v00.v[k] + tx.l1 * v01.v[k]) + ty.l1 * (tx.l0 * v10.v[k] + tx.l1 * v11.v[k]);
+    for (int k = 0; k < 16; ++k) r.v[k] += ty.l0 * (tx.l0 * v00.v[k] + tx.l1 * v01.v[k]) + ty.l1 * (tx.l0 * v10.v[k] + tx.l1 * v11.v[k]);
   }
   {
     const LinTap ty = lin_tap(y, (float)H5 / (float)H3, H5), tx = lin_tap(x, (float)W5 / (float)W3, W5);
     const int64_t bb = (int64_t)b * H5 * W5;
-    const F8 v00 = ld_split8(x5, bb + (int64_t)ty.i0 * W5 + tx.i0, c8), v01 = ld_split8(x5, bb + (int64_t)ty.i0 * W5 + tx.i1, c8);
-    const F8 v10 = ld_split8(x5, bb + (int64_t)ty.i1 * W5 + tx.i0, c8), v11 = ld_split8(x5, bb + (int64_t)ty.i1 * W5 + tx.i1, c8);
+    const F16v v00 = ld_split16(x5, bb + (int64_t)ty.i0 * W5 + tx.i0, c16), v01 = ld_split16(x5, bb + (int64_t)ty.i0 * W5 + tx.i1, c16);
+    const F16v v10 = ld_split16(x5, bb + (int64_t)ty.i1 * W5 + tx.i0, c16), v11 = ld_split16(x5, bb + (int64_t)ty.i1 * W5 + tx.i1, c16);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r.v[k] += ty.l0 * (tx.l0 * v00.v[k] + tx.l1 * v01.v[k]) + ty.l1 * (tx.l0 * v10.v[k] + tx.l1 * v11.v[k]);
+    for (int k = 0; k < 16; ++k) r.v[k] += ty.l0 * (tx.l0 * v00.v[k] + tx.l1 * v01.v[k]) + ty.l1 * (tx.l0 * v10.v[k] + tx.l1 * v11.v[k]);
   }
-  uint32_t hw[4], lw[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const __half2 h = __floats2half2_rn(r.v[2 * k], r.v[2 * k + 1]);
-    const float2 f = __half22float2(h);
-    const __half2 l = __floats2half2_rn(r.v[2 * k] - f.x, r.v[2 * k + 1] - f.y);
-    hw[k] = *reinterpret_cast<const uint32_t*>(&h);
-    lw[k] = *reinterpret_cast<const uint32_t*>(&l);
-  }
-  __half* sp = out_split + (i >> 3) * 128 + c8 * 8;
-  *reinterpret_cast<uint4*>(sp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-  *reinterpret_cast<uint4*>(sp + 64) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  __half* hp = out_split + (i >> 2) * 128 + c16 * 16;
+  tc::store_split_row<16>(hp, hp + 64, r.v);
 }
 
 int launch_fuse_pyramid_split(const __half* x3, const __half* x4, const __half* x5, __half* out_split, int B, int H3, int W3,
                               cudaStream_t st) {
-  const int64_t total8 = (int64_t)B * H3 * W3 * 8;
-  fuse_pyramid_split_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, st>>>(x3, x4, x5, out_split, H3, W3, H3 / 2, W3 / 2, H3 / 4,
-                                                                               W3 / 4, total8);
+  const int64_t total16 = (int64_t)B * H3 * W3 * 4;
+  fuse_pyramid_split_kernel<<<(unsigned)((total16 + 255) / 256), 256, 0, st>>>(x3, x4, x5, out_split, H3, W3, H3 / 2, W3 / 2, H3 / 4,
+                                                                                W3 / 4, total16);
   XF_LAUNCH_CHECK();
   return XF_OK;
 }

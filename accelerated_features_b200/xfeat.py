@@ -373,6 +373,23 @@ class XFeat(torch.nn.Module):
         Host inputs travel through the pinned copy pipeline of match_xfeat_stream."""
         return next(self.match_xfeat_stream([(imgs1, imgs2)], top_k=top_k, min_cossim=min_cossim))
 
+    @torch.inference_mode()
+    def match_xfeat_verified_batch(self, imgs1, imgs2, top_k=None, min_cossim=-1, ransac_thr: float = 3.0, iters: int = 1024,
+                                   seed: int = 0) -> List[Dict[str, np.ndarray]]:
+        """match_xfeat_batch followed, still on the device, by the homography RANSAC the reference's callers run on the matches
+        (cv2.findHomography(..., USAC_MAGSAC, thr) in realtime_demo.py:225): per pair {'mkpts0', 'mkpts1' (N,2), 'H' (3,3),
+        'inliers' (N,) bool}.  One host synchronisation for the whole batch."""
+        from .geometry import find_homography_batch
+        if top_k is None: top_k = self.top_k
+        x1, d1 = self._parse_input(imgs1)
+        x2, d2 = self._parse_input(imgs2)
+        mk0, mk1, cnt = self._match_sparse_batch_device(x1, x2, top_k, min_cossim, div255=(d1, d2))
+        H, mask, _ = find_homography_batch(mk0, mk1, cnt, ransac_thr, iters, seed)
+        c = cnt.tolist()
+        self._check_counts(c, "match_xfeat_verified_batch")
+        mk0, mk1, H, mask = mk0.cpu().numpy(), mk1.cpu().numpy(), H.cpu().numpy(), mask.cpu().numpy()
+        return [{"mkpts0": mk0[b, :c[b]], "mkpts1": mk1[b, :c[b]], "H": H[b], "inliers": mask[b, :c[b]]} for b in range(len(c))]
+
     # ------------------------------------------------------------------------------------------------------------
     # streaming: pinned, double-buffered host -> device -> host pipeline (SURVEY 8f-1)
     # ------------------------------------------------------------------------------------------------------------

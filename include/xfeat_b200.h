@@ -205,6 +205,22 @@ XF_API int xfeat_subpix_softmax2d(const float* d_maps, int64_t n, float temp, fl
 XF_API size_t xfeat_fine_matcher_workspace_bytes(int n);
 XF_API int xfeat_fine_matcher(xfeat_ctx* ctx, const float* d_x, int n, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Geometric verification right after the path
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* replaces: cv2.findHomography(pts1, pts2, cv2.USAC_MAGSAC, thr, maxIters, confidence) as called on the matches by
+ * realtime_demo.py:225 and the notebooks (the estimator itself lives in un-vendored OpenCV).  For every pair b:
+ * d_pts0 / d_pts1 (batch, n_max, 2) matched coordinates (e.g. the outputs of xfeat_gather_matches), d_n (batch) counts (NULL:
+ * n_max each).  `iters` minimal 4-point hypotheses per pair, scored on all correspondences (MSAC, forward transfer error in
+ * pixels of image 1 against thr_px), best one re-fitted twice by least squares on its inliers.  Outputs: d_H (batch, 9)
+ * row-major with H[8] = 1, d_inliers (batch, n_max) 0/1, d_n_inliers (batch).  Fewer than 4 matches: identity, no inliers.
+ * n_max <= 8192.  Deterministic for a given seed. */
+XF_API size_t xfeat_ransac_workspace_bytes(int batch, int iters);
+XF_API int xfeat_ransac_homography(const float* d_pts0, const float* d_pts1, const int32_t* d_n, int n_max, int batch,
+                                   float thr_px, int iters, uint32_t seed, float* d_H, uint8_t* d_inliers,
+                                   int32_t* d_n_inliers, void* d_ws, size_t ws_bytes, void* stream);
+
 /* Test hook: run one folded conv layer of the packed table (index into csrc/layers.h) through the generic
  * kernels. in (B,Hi,Wi,Cin) NHWC -> out (B,Ho,Wo,Cout). */
 XF_API int xfeat_debug_conv_layer(xfeat_ctx* ctx, int layer, const float* d_in, int B, int Hi, int Wi, float* d_out,

@@ -91,3 +91,18 @@ def test_heatmap_unshuffle_rule():
     p = F.softmax(k, 1)
     for (i, j, h, w) in [(0, 0, 0, 0), (2, 7, 1, 3), (7, 1, 2, 0)]:
         assert heat[0, 0, 8 * h + i, 8 * w + j] == p[0, 8 * i + j, h, w]
+
+
+def test_eval_metrics_restatement():
+    """evalharness restates megadepth1500.py's metric functions (the reference module imports poselib, absent here)."""
+    from accelerated_features_b200 import evalharness as ev
+    auc = ev.error_auc([1, 2, 30, 4, 50])
+    assert abs(auc["auc@5"] - 0.4) < 1e-12 and abs(auc["auc@10"] - 0.5) < 1e-12 and abs(auc["auc@20"] - 0.55) < 1e-12
+    T = np.eye(4)
+    T[:3, 3] = [1.0, 0.0, 0.0]
+    c, s = np.cos(np.deg2rad(10.0)), np.sin(np.deg2rad(10.0))
+    R = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    t_err, r_err = ev.relative_pose_error(T, R, np.array([-2.0, 0.0, 0.0]))      # sign of t is not observable
+    assert abs(t_err) < 1e-6 and abs(r_err - 10.0) < 1e-6
+    m = ev.compute_maa([{"t_err": 1.0, "R_err": 3.0}, {"t_err": 30.0, "R_err": 2.0}])
+    assert m["mAcc@5"] == 0.5 and m["mAcc@20"] == 0.5
