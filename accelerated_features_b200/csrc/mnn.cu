@@ -9,6 +9,7 @@
 // min_cossim threshold and an ordered compaction (idx0 ascending, as boolean-mask indexing gives in the reference).
 //
 // fp32 FFMA (exact fp32 products, fp32 accumulate) -- the precision the integer outputs are specified against.
+#include <cuda_fp16.h>
 #include <cub/block/block_scan.cuh>
 
 #include "common.cuh"
@@ -239,6 +240,9 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
 // default.
 static int g_mnn_impl = 1;
 size_t mnn_fast_workspace_bytes(int batch, int n1_max, int n2_max);
+int launch_mnn_tc_presplit(const __half* f1s, const int* n1, int n1_max, const __half* f2s, const int* n2, int n2_max, int n_pad,
+                           int batch, int scale_log2, void* d_ws, size_t ws_bytes, unsigned long long** best12,
+                           unsigned long long** best21, float** inv_s2, cudaStream_t st, int pairs_kernel);
 int launch_mnn_fast(const float* f1, const int* n1, int n1_max, int64_t stride1, const float* f2, const int* n2, int n2_max,
                     int64_t stride2, int batch, void* d_ws, size_t ws_bytes, unsigned long long** best12,
                     unsigned long long** best21, float** inv_s2, cudaStream_t st, float abs_bound, int sm_count);
@@ -316,6 +320,36 @@ extern "C" int xfeat_mnn_match_bounded(const float* d_f1, const int32_t* d_n1, i
   XF_LAUNCH_CHECK();
   xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(ws.row_best, ws.col_best, d_n1, d_n2, n1_max, n2_max, min_cossim, nullptr,
                                                   (long long*)d_idx0, (long long*)d_idx1, d_n_matches);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+extern "C" size_t xfeat_mnn_presplit_workspace_bytes(int batch, int n1_max, int n2_max) {
+  xf::Bump bump(nullptr, 0);
+  bump.take<unsigned long long>((size_t)batch * n1_max);
+  bump.take<unsigned long long>((size_t)batch * n2_max);
+  bump.take<float>(1);
+  return bump.used();
+}
+
+extern "C" int xfeat_mnn_match_presplit(const void* d_f1s, const int32_t* d_n1, int n1_max, const void* d_f2s, const int32_t* d_n2,
+                                        int n2_max, int n_pad, int batch, int scale_log2, float min_cossim, int64_t* d_idx0,
+                                        int64_t* d_idx1, int32_t* d_n_matches, void* d_ws, size_t ws_bytes, void* stream) {
+  XF_REQUIRE(d_f1s && d_f2s && d_idx0 && d_idx1 && d_n_matches && d_ws, "mnn_match_presplit: null pointer");
+  XF_REQUIRE(batch > 0 && batch <= 65535 && n1_max > 0 && n2_max > 0, "mnn_match_presplit: bad sizes");
+  XF_REQUIRE(((uintptr_t)d_f1s % 128) == 0 && ((uintptr_t)d_f2s % 128) == 0, "mnn_match_presplit: operands must be 128-byte aligned");
+  if (xf::g_mnn_impl != 1 && xf::g_mnn_impl != 3) {
+    xf::set_error("mnn_match_presplit: implementation %d does not take pre-split operands (1 and 3 do)", xf::g_mnn_impl);
+    return XF_E_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long *b12 = nullptr, *b21 = nullptr;
+  float* inv_s2 = nullptr;
+  int rc = xf::launch_mnn_tc_presplit((const __half*)d_f1s, d_n1, n1_max, (const __half*)d_f2s, d_n2, n2_max, n_pad, batch,
+                                      scale_log2, d_ws, ws_bytes, &b12, &b21, &inv_s2, st, xf::g_mnn_impl == 3);
+  if (rc) return rc;
+  xf::mnn_finalize_kernel<<<batch, 1024, 0, st>>>(b12, b21, d_n1, d_n2, n1_max, n2_max, min_cossim, inv_s2, (long long*)d_idx0,
+                                                  (long long*)d_idx1, d_n_matches);
   XF_LAUNCH_CHECK();
   return XF_OK;
 }

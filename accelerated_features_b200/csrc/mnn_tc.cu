@@ -858,6 +858,44 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
   return XF_OK;
 }
 
+int launch_mnn_tc_rows(const __half* a0, const __half* b0, const __half* a1, const __half* b1, const int* n1, int n1_max,
+                       const int* n2, int n2_max, int n_pad, int batch, const int* rows_cnt, const int* row_map,
+                       unsigned long long* best12, unsigned long long* best21, cudaStream_t st);
+__global__ void set_scalar_kernel(float* p, float v) { *p = v; }
+
+// Operands already split by the producer (xfeat_detect_sparse_split): (batch * n_pad) rows x 128 halves each, scaled by 2^scale_log2.
+int launch_mnn_tc_presplit(const __half* f1s, const int* n1, int n1_max, const __half* f2s, const int* n2, int n2_max, int n_pad,
+                           int batch, int scale_log2, void* d_ws, size_t ws_bytes, unsigned long long** best12,
+                           unsigned long long** best21, float** inv_s2, cudaStream_t st, int pairs_kernel) {
+  XF_REQUIRE(n_pad % (2 * TC_ROWS) == 0 && n_pad >= n1_max && n_pad >= n2_max, "mnn_match_presplit: n_pad must be a multiple of %d covering both sets", 2 * TC_ROWS);
+  XF_REQUIRE((int64_t)batch * n_pad < (1ll << 31), "mnn_match_presplit: batch * n too large");
+  Bump bump(d_ws, ws_bytes);
+  unsigned long long* b12 = bump.take<unsigned long long>((size_t)batch * n1_max);
+  unsigned long long* b21 = bump.take<unsigned long long>((size_t)batch * n2_max);
+  float* scale = bump.take<float>(1);
+  if (!bump.ok) {
+    set_error("mnn_match_presplit: workspace too small (%zu < %zu)", ws_bytes, bump.used());
+    return XF_E_WORKSPACE;
+  }
+  XF_CUDA(cudaMemsetAsync(b12, 0, sizeof(unsigned long long) * (size_t)batch * n1_max, st));
+  XF_CUDA(cudaMemsetAsync(b21, 0, sizeof(unsigned long long) * (size_t)batch * n2_max, st));
+  set_scalar_kernel<<<1, 1, 0, st>>>(scale, ldexpf(1.f, -2 * scale_log2));
+  XF_LAUNCH_CHECK();
+  *best12 = b12; *best21 = b21; *inv_s2 = scale;
+  if (pairs_kernel) {
+    TcMaps maps;
+    int rc;
+    if ((rc = make_map(&maps.m1, f1s, (uint64_t)batch * n_pad))) return rc;
+    if ((rc = make_map(&maps.m2, f2s, (uint64_t)batch * n_pad))) return rc;
+    XF_DYN_SMEM(mnn_tc2_kernel, TC2_SMEM);
+    dim3 grid2(n_pad / TC_ROWS, batch, 2);
+    mnn_tc2_kernel<<<grid2, TC_THREADS, TC2_SMEM, st>>>(maps, n1, n1_max, n2, n2_max, n_pad, b12, b21);
+    XF_LAUNCH_CHECK();
+    return XF_OK;
+  }
+  return launch_mnn_tc_rows(f1s, f2s, f2s, f1s, n1, n1_max, n2, n2_max, n_pad, batch, nullptr, nullptr, b12, b21, st);
+}
+
 int launch_absmax(const float* f, const int* np, int n_max, int64_t stride, int batch, unsigned* out, cudaStream_t st) {
   absmax_kernel<<<dim3(8, batch), 256, 0, st>>>(f, np, n_max, stride, out);
   XF_LAUNCH_CHECK();

@@ -349,6 +349,248 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_h_final_kernel(const float*
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Essential matrix (calibrated relative pose; the estimator the 1500-pair benchmarks call through poselib,
+// modules/eval/megadepth1500.py:98-113).  Inputs are NORMALISED image coordinates (K^-1 applied by the caller); the minimal
+// solver is the normalised 8-point algorithm projected onto the essential manifold (singular values (1,1,0)), scored with the
+// Sampson distance.  (poselib uses the 5-point solver, which also handles planar scenes; the 8-point form does not -- see
+// DESIGN.md.)  Every LANE solves its own hypothesis (a 9x9 and a 3x3 symmetric eigen-problem in fp64), then the warp scores the
+// 32 hypotheses one after the other.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ void rs_project_essential(double (&E)[9]) {
+  // E = U diag(s) V^T;  V and s^2 from the eigen-decomposition of E^T E, then E' = (E v1) v1^T / |E v1| ... with s = (1,1,0):
+  // E' = u1 v1^T + u2 v2^T where (v1, v2) are the two leading right singular vectors and u_i = E v_i / s_i.
+  double M[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) { M[i][j] = E[0 + i] * E[0 + j] + E[3 + i] * E[3 + j] + E[6 + i] * E[6 + j]; V[i][j] = (i == j); }
+  for (int sweep = 0; sweep < 20; ++sweep) {
+    const double off = M[0][1] * M[0][1] + M[0][2] * M[0][2] + M[1][2] * M[1][2];
+    if (off < 1e-30) break;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (fabs(M[p][q]) < 1e-300) continue;
+        const double theta = (M[q][q] - M[p][p]) / (2.0 * M[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; ++k) { const double a = M[k][p], b = M[k][q]; M[k][p] = c * a - sn * b; M[k][q] = sn * a + c * b; }
+        for (int k = 0; k < 3; ++k) { const double a = M[p][k], b = M[q][k]; M[p][k] = c * a - sn * b; M[q][k] = sn * a + c * b; }
+        for (int k = 0; k < 3; ++k) { const double a = V[k][p], b = V[k][q]; V[k][p] = c * a - sn * b; V[k][q] = sn * a + c * b; }
+      }
+  }
+  int lo = 0;                                   // column of the smallest eigenvalue: dropped
+  for (int i = 1; i < 3; ++i)
+    if (M[i][i] < M[lo][lo]) lo = i;
+  double out[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int c = 0; c < 3; ++c) {
+    if (c == lo) continue;
+    double u[3];
+    for (int r = 0; r < 3; ++r) u[r] = E[3 * r] * V[0][c] + E[3 * r + 1] * V[1][c] + E[3 * r + 2] * V[2][c];
+    const double nrm = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+    if (nrm < 1e-300) continue;
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) out[3 * r + k] += (u[r] / nrm) * V[k][c];
+  }
+  for (int k = 0; k < 9; ++k) E[k] = out[k];
+}
+
+// squared Sampson distance of (x,y) <-> (u,v) under x1^T E x0 = 0
+__device__ __forceinline__ float rs_sampson2(const float (&E)[9], float x, float y, float u, float v) {
+  const float a = E[0] * x + E[1] * y + E[2], b = E[3] * x + E[4] * y + E[5], c = E[6] * x + E[7] * y + E[8];
+  const float d = E[0] * u + E[3] * v + E[6], f = E[1] * u + E[4] * v + E[7];
+  const float e = u * a + v * b + c;
+  const float den = a * a + b * b + d * d + f * f;
+  return den > 1e-20f ? e * e / den : 1e30f;
+}
+
+__device__ __forceinline__ void rs_epi_row(float x, float y, float u, float v, double (&r)[9]) {
+  r[0] = (double)u * x; r[1] = (double)u * y; r[2] = u; r[3] = (double)v * x; r[4] = (double)v * y; r[5] = v; r[6] = x; r[7] = y; r[8] = 1.0;
+}
+
+__global__ void __launch_bounds__(RS_THREADS) ransac_e_hyp_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                                                  const int* __restrict__ np, int n_max, float thr,
+                                                                  int rounds_per_warp, uint32_t seed, RsRecord* __restrict__ best) {
+  extern __shared__ float4 sPts[];                 // (x, y, u, v): already normalised image coordinates
+  __shared__ RsRecord sBest[RS_WARPS];
+  const int pair = blockIdx.y;
+  const int n = min(np ? np[pair] : n_max, min(n_max, RS_MAX_PTS));
+  RsRecord mine;
+  mine.cost = 3.0e38f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) mine.m[k] = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (n >= 8) {
+    const float* q0 = p0 + (int64_t)pair * n_max * 2;
+    const float* q1 = p1 + (int64_t)pair * n_max * 2;
+    for (int i = threadIdx.x; i < n; i += RS_THREADS) sPts[i] = make_float4(q0[2 * i], q0[2 * i + 1], q1[2 * i], q1[2 * i + 1]);
+    __syncthreads();
+    const float t2 = thr * thr;
+    for (int rd = 0; rd < rounds_per_warp; ++rd) {
+      // every lane: one 8-point hypothesis
+      const uint32_t hid = (uint32_t)(((blockIdx.x * RS_WARPS + warp) * rounds_per_warp + rd) * 32 + lane);
+      uint32_t s = rs_hash(seed ^ (0x9e3779b9u * (uint32_t)(pair + 1)) ^ (0x85ebca6bu * (hid + 1)));
+      int idx[8];
+      for (int k = 0; k < 8; ++k) {
+        bool dup;
+        do {
+          s = rs_hash(s + 0x6d2b79f5u);
+          idx[k] = (int)(((uint64_t)s * (uint64_t)n) >> 32);
+          dup = false;
+          for (int j = 0; j < k; ++j) dup |= (idx[j] == idx[k]);
+        } while (dup);
+      }
+      double M[9][9];
+      for (int a = 0; a < 9; ++a)
+        for (int b2 = 0; b2 < 9; ++b2) M[a][b2] = 0.0;
+      for (int k = 0; k < 8; ++k) {
+        const float4 c = sPts[idx[k]];
+        double r[9];
+        rs_epi_row(c.x, c.y, c.z, c.w, r);
+        for (int a = 0; a < 9; ++a)
+          for (int b2 = a; b2 < 9; ++b2) M[a][b2] += r[a] * r[b2];
+      }
+      for (int a = 0; a < 9; ++a)
+        for (int b2 = 0; b2 < a; ++b2) M[a][b2] = M[b2][a];
+      double e[9];
+      rs_smallest_eigvec<9>(M, e);
+      rs_project_essential(e);
+      float Ef[9];
+      for (int k = 0; k < 9; ++k) Ef[k] = (float)e[k];
+      // the warp scores the 32 hypotheses one after the other
+      for (int src = 0; src < 32; ++src) {
+        float E[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) E[k] = __shfl_sync(0xffffffffu, Ef[k], src);
+        float cost = 0.f;
+        for (int i = lane; i < n; i += 32) {
+          const float4 c = sPts[i];
+          cost += fminf(rs_sampson2(E, c.x, c.y, c.z, c.w), t2);
+        }
+        for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+        if (cost < mine.cost) {
+          mine.cost = cost;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) mine.m[k] = E[k];
+        }
+      }
+    }
+  }
+  if (lane == 0) sBest[warp] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    RsRecord b = sBest[0];
+    for (int w = 1; w < RS_WARPS; ++w)
+      if (sBest[w].cost < b.cost) b = sBest[w];
+    best[(int64_t)pair * gridDim.x + blockIdx.x] = b;
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS) ransac_e_final_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                                                    const int* __restrict__ np, int n_max, float thr,
+                                                                    const RsRecord* __restrict__ best, int blocks_per_pair,
+                                                                    float* __restrict__ E_out, unsigned char* __restrict__ mask,
+                                                                    int* __restrict__ n_inl) {
+  extern __shared__ float4 sPts[];
+  __shared__ double sAcc[RS_WARPS][45];
+  __shared__ float sE[9];
+  __shared__ int sCnt;
+  const int pair = blockIdx.x;
+  const int n_all = np ? np[pair] : n_max;
+  const int n = min(n_all, min(n_max, RS_MAX_PTS));
+  unsigned char* mk = mask + (int64_t)pair * n_max;
+  for (int i = threadIdx.x; i < n_max; i += RS_THREADS) mk[i] = 0;
+  if (n < 8) {
+    if (threadIdx.x == 0) {
+      n_inl[pair] = n_all < 0 ? n_all : 0;
+      for (int k = 0; k < 9; ++k) E_out[pair * 9 + k] = 0.f;
+    }
+    return;
+  }
+  const float* q0 = p0 + (int64_t)pair * n_max * 2;
+  const float* q1 = p1 + (int64_t)pair * n_max * 2;
+  for (int i = threadIdx.x; i < n; i += RS_THREADS) sPts[i] = make_float4(q0[2 * i], q0[2 * i + 1], q1[2 * i], q1[2 * i + 1]);
+  if (threadIdx.x == 0) {
+    RsRecord b = best[(int64_t)pair * blocks_per_pair];
+    for (int k = 1; k < blocks_per_pair; ++k) {
+      const RsRecord c = best[(int64_t)pair * blocks_per_pair + k];
+      if (c.cost < b.cost) b = c;
+    }
+    for (int k = 0; k < 9; ++k) sE[k] = b.m[k];
+  }
+  __syncthreads();
+  const float t2 = thr * thr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int round = 0; round < 2; ++round) {
+    float E[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) E[k] = sE[k];
+    double acc[45];
+#pragma unroll
+    for (int k = 0; k < 45; ++k) acc[k] = 0.0;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+      const float4 c = sPts[i];
+      if (rs_sampson2(E, c.x, c.y, c.z, c.w) < t2) {
+        ++cnt;
+        double r[9];
+        rs_epi_row(c.x, c.y, c.z, c.w, r);
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 9; ++a)
+#pragma unroll
+          for (int b2 = a; b2 < 9; ++b2) acc[e++] += r[a] * r[b2];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 45; ++k) {
+      double v = acc[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sAcc[warp][k] = v;
+    }
+    const int total = __syncthreads_count(0) + 0;   // barrier
+    (void)total;
+    if (threadIdx.x == 0) sCnt = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) atomicAdd(&sCnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0 && sCnt >= 8) {
+      double M[9][9], vec[9];
+      int e = 0;
+      for (int a = 0; a < 9; ++a)
+        for (int b2 = a; b2 < 9; ++b2) {
+          double v = 0.0;
+          for (int w = 0; w < RS_WARPS; ++w) v += sAcc[w][e];
+          M[a][b2] = v; M[b2][a] = v;
+          ++e;
+        }
+      rs_smallest_eigvec<9>(M, vec);
+      rs_project_essential(vec);
+      for (int k = 0; k < 9; ++k) sE[k] = (float)vec[k];
+    }
+    __syncthreads();
+  }
+  float E[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) E[k] = sE[k];
+  int cnt = 0;
+  for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+    const float4 c = sPts[i];
+    const bool in = rs_sampson2(E, c.x, c.y, c.z, c.w) < t2;
+    mk[i] = in ? 1 : 0;
+    cnt += in ? 1 : 0;
+  }
+  if (threadIdx.x == 0) sCnt = 0;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) atomicAdd(&sCnt, cnt);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    n_inl[pair] = sCnt;
+    for (int k = 0; k < 9; ++k) E_out[pair * 9 + k] = E[k];
+  }
+}
+
 }  // namespace xf
 
 extern "C" size_t xfeat_ransac_workspace_bytes(int batch, int iters) {
@@ -374,6 +616,28 @@ extern "C" int xfeat_ransac_homography(const float* d_pts0, const float* d_pts1,
   XF_LAUNCH_CHECK();
   xf::ransac_h_final_kernel<<<batch, xf::RS_THREADS, smem, st>>>(d_pts0, d_pts1, d_n, n_max, thr_px, (const xf::RsRecord*)d_ws, bpp,
                                                                  d_H, d_inliers, d_n_inliers);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
+extern "C" int xfeat_ransac_essential(const float* d_x0, const float* d_x1, const int32_t* d_n, int n_max, int batch, float thr,
+                                      int iters, uint32_t seed, float* d_E, uint8_t* d_inliers, int32_t* d_n_inliers, void* d_ws,
+                                      size_t ws_bytes, void* stream) {
+  XF_REQUIRE(d_x0 && d_x1 && d_E && d_inliers && d_n_inliers && d_ws, "ransac_essential: null pointer");
+  XF_REQUIRE(batch > 0 && batch <= 65535 && n_max > 0 && n_max <= xf::RS_MAX_PTS && iters > 0 && thr > 0.f,
+             "ransac_essential: bad arguments (n_max <= %d)", xf::RS_MAX_PTS);
+  XF_REQUIRE(ws_bytes >= xfeat_ransac_workspace_bytes(batch, iters), "ransac_essential: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int bpp = xf::cdiv(iters, xf::RS_WARPS * 32);          // one round = 32 hypotheses per warp
+  const int rounds = xf::cdiv(iters, bpp * xf::RS_WARPS * 32);
+  const size_t smem = (size_t)n_max * sizeof(float4);
+  XF_DYN_SMEM(xf::ransac_e_hyp_kernel, smem);
+  XF_DYN_SMEM(xf::ransac_e_final_kernel, smem);
+  xf::ransac_e_hyp_kernel<<<dim3(bpp, batch), xf::RS_THREADS, smem, st>>>(d_x0, d_x1, d_n, n_max, thr, rounds, seed,
+                                                                          (xf::RsRecord*)d_ws);
+  XF_LAUNCH_CHECK();
+  xf::ransac_e_final_kernel<<<batch, xf::RS_THREADS, smem, st>>>(d_x0, d_x1, d_n, n_max, thr, (const xf::RsRecord*)d_ws, bpp, d_E,
+                                                                 d_inliers, d_n_inliers);
   XF_LAUNCH_CHECK();
   return XF_OK;
 }

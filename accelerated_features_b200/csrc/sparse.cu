@@ -9,6 +9,9 @@
 
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+#include <cub/block/block_scan.cuh>
+
 #include "common.cuh"
 
 namespace xf {
@@ -300,6 +303,92 @@ __global__ void __launch_bounds__(NM_WARPS * 32, 5) nms_march_kernel(const float
     if (gbase + i < cap) keys[(int64_t)b * cap + gbase + i] = sKeys[i];
 }
 
+
+// Per-image top-k of the NMS candidates, sorted (replaces the capacity-wide cub segmented sort for top_k <= 8192: the sort
+// handled every candidate -- 20-30 k per noise image -- to keep 4096).  One CTA per image:
+//   1. radix select (11-bit digits, most significant first) of the k-th largest 64-bit key; keys are unique (the pixel index sits
+//      in the low word), so the k largest are exactly the keys >= that threshold;  2. compaction of those k keys into shared
+//   memory;  3. bitonic sort, descending.  Same order as the cub sort: (score desc, raster index asc).
+constexpr int TS_THREADS = 1024, TS_BITS = 11, TS_BINS = 1 << TS_BITS;
+
+__global__ void __launch_bounds__(TS_THREADS) topk_select_sort_kernel(const unsigned long long* __restrict__ keys,
+                                                                      const int* __restrict__ n_keep, int cap, int top_k, int P,
+                                                                      unsigned long long* __restrict__ sorted) {
+  extern __shared__ unsigned long long sK[];   // [P], P = power of two >= top_k
+  __shared__ int sHist[TS_BINS];
+  __shared__ int sSel[2];                      // chosen digit, keys taken from the digits above it
+  __shared__ int sCnt;
+  using Scan = cub::BlockScan<int, TS_THREADS>;
+  __shared__ typename Scan::TempStorage scan_tmp;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int nk = n_keep[b];
+  if (nk > cap) return;                        // candidate overflow: the sampler reports XF_N_OVERFLOW and reads nothing
+  const int n = nk, k = min(n, top_k);
+  const unsigned long long* kb = keys + (int64_t)b * cap;
+  for (int i = tid; i < P; i += TS_THREADS) sK[i] = 0ull;
+  __syncthreads();
+  if (n <= top_k) {
+    for (int i = tid; i < n; i += TS_THREADS) sK[i] = kb[i];
+  } else {
+    unsigned long long prefix = 0ull;          // digits chosen so far (the high 64 - shift bits of the threshold)
+    int remaining = k, shift = 64;
+    unsigned long long sel_val = 0ull;
+    int sel_shift = 0;
+    while (true) {
+      const int bits = (shift >= TS_BITS) ? TS_BITS : shift;
+      const int hi_shift = shift;              // keys must agree with `prefix` above this bit
+      shift -= bits;
+      for (int i = tid; i < TS_BINS; i += TS_THREADS) sHist[i] = 0;
+      __syncthreads();
+      const unsigned mask = (1u << bits) - 1u;
+      for (int i = tid; i < n; i += TS_THREADS) {
+        const unsigned long long key = kb[i];
+        if (hi_shift == 64 || (key >> hi_shift) == prefix) atomicAdd(&sHist[(unsigned)(key >> shift) & mask], 1);
+      }
+      __syncthreads();
+      // from the largest digit down: first digit D whose cumulative count reaches `remaining`
+      const int r0 = 2 * tid, r1 = 2 * tid + 1;                       // reversed bin indices (0 = largest digit)
+      const int c0 = sHist[TS_BINS - 1 - r0], c1 = sHist[TS_BINS - 1 - r1];
+      int excl, total;
+      Scan(scan_tmp).ExclusiveSum(c0 + c1, excl, total);
+      if (excl < remaining && excl + c0 >= remaining) { sSel[0] = TS_BINS - 1 - r0; sSel[1] = excl; }
+      else if (excl + c0 < remaining && excl + c0 + c1 >= remaining) { sSel[0] = TS_BINS - 1 - r1; sSel[1] = excl + c0; }
+      __syncthreads();
+      const int D = sSel[0], need = remaining - sSel[1], have = sHist[D];
+      prefix = (prefix << bits) | (unsigned long long)D;
+      __syncthreads();                          // sHist / sSel are rewritten by the next round
+      if (need == have || shift == 0) {         // the whole bucket is wanted: the threshold is settled at this digit
+        sel_val = prefix;
+        sel_shift = shift;
+        break;
+      }
+      remaining = need;
+    }
+    if (tid == 0) sCnt = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += TS_THREADS) {
+      const unsigned long long key = kb[i];
+      if ((key >> sel_shift) >= sel_val) {
+        const int pos = atomicAdd(&sCnt, 1);
+        if (pos < P) sK[pos] = key;
+      }
+    }
+  }
+  // bitonic sort, descending
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = tid; t < (P >> 1); t += TS_THREADS) {
+        const int i = 2 * t - (t & (stride - 1)), j = i + stride;
+        const bool desc = ((i & size) == 0);
+        const unsigned long long a = sK[i], c = sK[j];
+        if ((a < c) == desc) { sK[i] = c; sK[j] = a; }
+      }
+    }
+  __syncthreads();
+  for (int r = tid; r < k; r += TS_THREADS) sorted[(int64_t)b * cap + r] = sK[r];
+}
+
 __global__ void segment_offsets_kernel(const int* __restrict__ counts, int cap, int B, int* __restrict__ begin,
                                        int* __restrict__ end) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,13 +481,26 @@ __device__ __forceinline__ float4 bicubic4(const float* __restrict__ fb, const f
 }
 
 // Half a warp per output slot (b, r): lane owns 4 channels. feats: (B,Hm,Wm,64) NHWC un-normalised, den: (B,Hm,Wm).
+// The matcher's operand row of a unit-norm descriptor: x * 2^13 = hi + lo in fp16, [hi(64) | lo(64)] (mnn_tc.cu, abs_bound = 1).
+// Written next to the fp32 descriptor so xfeat_mnn_match_presplit needs no max-reduction / split pass over the descriptors.
+constexpr float kDescSplitScale = 8192.0f;
+__device__ __forceinline__ void store_desc_split(__half* sp, const float4& d) {
+  const float x0 = d.x * kDescSplitScale, x1 = d.y * kDescSplitScale, x2 = d.z * kDescSplitScale, x3 = d.w * kDescSplitScale;
+  const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(x0 - f0.x, x1 - f0.y), l1 = __floats2half2_rn(x2 - f1.x, x3 - f1.y);
+  *reinterpret_cast<uint2*>(sp) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  *reinterpret_cast<uint2*>(sp + 64) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
 // Generic kernel (any top_k): slots are visited in score order, so taps of neighbouring keypoints rarely share L1 lines.
 __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long long* __restrict__ sorted,
                                                           const int* __restrict__ n_keep, const float* __restrict__ feats,
                                                           const float* __restrict__ den, int B, int H, int W, int Hm, int Wm,
                                                           int cap, int top_k, float rw, float rh, float* __restrict__ kpts,
                                                           float* __restrict__ scores, float* __restrict__ desc,
-                                                          int* __restrict__ n_valid, int* __restrict__ kpts_int) {
+                                                          int* __restrict__ n_valid, int* __restrict__ kpts_int,
+                                                          __half* __restrict__ desc_split, int split_rows) {
   const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
   const int l16 = threadIdx.x & 15;
   const int64_t total = (int64_t)B * top_k;
@@ -423,8 +525,10 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
   for (int s = 8; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
   if (!live) return;
   float4* dp = reinterpret_cast<float4*>(desc + slot * 64) + l16;
+  __half* sp = desc_split ? desc_split + ((int64_t)b * split_rows + r) * 128 + l16 * 4 : nullptr;
   if (!valid) {
     *dp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sp) { *reinterpret_cast<uint2*>(sp) = make_uint2(0u, 0u); *reinterpret_cast<uint2*>(sp + 64) = make_uint2(0u, 0u); }
     if (l16 == 0) {
       kpts[slot * 2] = 0.f; kpts[slot * 2 + 1] = 0.f; scores[slot] = 0.f;
       if (kpts_int) { kpts_int[slot * 2] = 0; kpts_int[slot * 2 + 1] = 0; }
@@ -432,7 +536,9 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
     return;
   }
   const float dn = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));  // F.normalize(feats, dim=-1), xfeat.py:93
-  *dp = make_float4(o.x * dn, o.y * dn, o.z * dn, o.w * dn);
+  const float4 dv = make_float4(o.x * dn, o.y * dn, o.z * dn, o.w * dn);
+  *dp = dv;
+  if (sp) store_desc_split(sp, dv);
   if (l16 == 0) {
     kpts[slot * 2] = __fmul_rn((float)x, rw);  // mkpts * [rw, rh], xfeat.py:96
     kpts[slot * 2 + 1] = __fmul_rn((float)y, rh);
@@ -450,7 +556,8 @@ constexpr int SAMPLE_MAX_K = 8192, SAMPLE_THREADS = 1024, SAMPLE_MAX_ROWS = 512;
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
     const unsigned long long* __restrict__ sorted, const int* __restrict__ n_keep, const float* __restrict__ feats,
     const float* __restrict__ den, int H, int W, int Hm, int Wm, int cap, int top_k, float rw, float rh, float* __restrict__ kpts,
-    float* __restrict__ scores, float* __restrict__ desc, int* __restrict__ n_valid, int* __restrict__ kpts_int) {
+    float* __restrict__ scores, float* __restrict__ desc, int* __restrict__ n_valid, int* __restrict__ kpts_int,
+    __half* __restrict__ desc_split, int split_rows) {
   extern __shared__ unsigned char sm_raw[];
   unsigned long long* sKey = reinterpret_cast<unsigned long long*>(sm_raw);           // [top_k]
   unsigned short* sOrder = reinterpret_cast<unsigned short*>(sKey + top_k);            // [top_k]
@@ -506,7 +613,9 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
     if (valid) {
       const int64_t slot = (int64_t)b * top_k + r;
       const float dn = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));  // F.normalize(feats, dim=-1), xfeat.py:93
-      reinterpret_cast<float4*>(desc + slot * 64)[l16] = make_float4(o.x * dn, o.y * dn, o.z * dn, o.w * dn);
+      const float4 dv = make_float4(o.x * dn, o.y * dn, o.z * dn, o.w * dn);
+      reinterpret_cast<float4*>(desc + slot * 64)[l16] = dv;
+      if (desc_split) store_desc_split(desc_split + ((int64_t)b * split_rows + r) * 128 + l16 * 4, dv);
       if (l16 == 0) {
         kpts[slot * 2] = __fmul_rn((float)x, rw);  // mkpts * [rw, rh], xfeat.py:96
         kpts[slot * 2 + 1] = __fmul_rn((float)y, rh);
@@ -514,6 +623,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
         if (kpts_int) { kpts_int[slot * 2] = x; kpts_int[slot * 2 + 1] = y; }
       }
     }
+  }
+  if (desc_split) {   // rows past n_valid up to the matcher's row padding are zero operands
+    uint4* zp = reinterpret_cast<uint4*>(desc_split + ((int64_t)b * split_rows + nv) * 128);
+    for (int64_t e = tid; e < (int64_t)(split_rows - nv) * 16; e += SAMPLE_THREADS) zp[e] = make_uint4(0u, 0u, 0u, 0u);
   }
   // zero-fill the slots past n_valid
   for (int64_t e = (int64_t)nv * 16 + tid; e < (int64_t)top_k * 16; e += SAMPLE_THREADS) {
@@ -572,6 +685,17 @@ extern "C" int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const f
                                    int B, int H, int W, int top_k, float threshold, float rw, float rh, float* d_kpts,
                                    float* d_scores, float* d_desc, int32_t* d_n_valid, int32_t* d_n_cand,
                                    int32_t* d_kpts_int, void* d_ws, size_t ws_bytes, void* stream) {
+  return xfeat_detect_sparse_split(ctx, d_feats, d_heat, d_reliability, B, H, W, top_k, threshold, rw, rh, d_kpts, d_scores, d_desc,
+                                   d_n_valid, d_n_cand, d_kpts_int, nullptr, 0, d_ws, ws_bytes, stream);
+}
+
+extern "C" int xfeat_detect_sparse_split(xfeat_ctx* ctx, const float* d_feats, const float* d_heat, const float* d_reliability,
+                                         int B, int H, int W, int top_k, float threshold, float rw, float rh, float* d_kpts,
+                                         float* d_scores, float* d_desc, int32_t* d_n_valid, int32_t* d_n_cand,
+                                         int32_t* d_kpts_int, void* d_desc_split, int split_rows, void* d_ws, size_t ws_bytes,
+                                         void* stream) {
+  XF_REQUIRE(d_desc_split == nullptr || (split_rows >= top_k && split_rows % 512 == 0),
+             "detect_sparse: split_rows must be a multiple of 512 and >= top_k (got %d)", split_rows);
   XF_REQUIRE(ctx && d_feats && d_heat && d_reliability && d_kpts && d_scores && d_desc && d_n_valid && d_ws,
              "detect_sparse: null pointer");
   XF_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0 && top_k > 0,
@@ -601,11 +725,21 @@ extern "C" int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const f
                                                              ws.n_keep, ws.n_cand);
   }
   XF_LAUNCH_CHECK();
-  xf::segment_offsets_kernel<<<xf::cdiv(B, 128), 128, 0, st>>>(ws.n_keep, cap, B, ws.seg_begin, ws.seg_end);
-  XF_LAUNCH_CHECK();
-  size_t tb = ws.cub_bytes;
-  XF_CUDA(cub::DeviceSegmentedSort::SortKeysDescending(ws.cub_temp, tb, ws.keys, ws.sorted, B * cap, B, ws.seg_begin,
-                                                       ws.seg_end, st));
+  static const bool force_cub = getenv("XFEAT_TOPK_CUB") != nullptr;   // A/B switch: the capacity-wide segmented sort
+  if (!force_cub && top_k <= 8192) {
+    int P = 1;
+    while (P < top_k) P <<= 1;
+    const size_t smem_ts = (size_t)P * sizeof(unsigned long long);
+    XF_DYN_SMEM(xf::topk_select_sort_kernel, smem_ts);
+    xf::topk_select_sort_kernel<<<B, xf::TS_THREADS, smem_ts, st>>>(ws.keys, ws.n_keep, cap, top_k, P, ws.sorted);
+    XF_LAUNCH_CHECK();
+  } else {
+    xf::segment_offsets_kernel<<<xf::cdiv(B, 128), 128, 0, st>>>(ws.n_keep, cap, B, ws.seg_begin, ws.seg_end);
+    XF_LAUNCH_CHECK();
+    size_t tb = ws.cub_bytes;
+    XF_CUDA(cub::DeviceSegmentedSort::SortKeysDescending(ws.cub_temp, tb, ws.keys, ws.sorted, B * cap, B, ws.seg_begin,
+                                                         ws.seg_end, st));
+  }
   const int64_t npix = (int64_t)B * Hm * Wm;
   xf::feat_norm_kernel<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, st>>>(d_feats, ws.den, npix);
   XF_LAUNCH_CHECK();
@@ -617,12 +751,14 @@ extern "C" int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const f
     XF_DYN_SMEM(xf::sample_desc_sorted_kernel, smem);
     xf::sample_desc_sorted_kernel<<<B, xf::SAMPLE_THREADS, smem, st>>>(ws.sorted, ws.n_keep, d_feats, ws.den, H, W, Hm, Wm, cap,
                                                                       top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid,
-                                                                      d_kpts_int);
+                                                                      d_kpts_int, (__half*)d_desc_split, split_rows);
   } else {
     const int64_t slots = (int64_t)B * top_k;
+    if (d_desc_split && split_rows > top_k)   // this kernel only visits the top_k slots: the matcher's padding rows are cleared here
+      XF_CUDA(cudaMemsetAsync(d_desc_split, 0, (size_t)B * split_rows * 128 * sizeof(__half), st));
     xf::sample_desc_kernel<<<(unsigned)((slots * 16 + 255) / 256), 256, 0, st>>>(
         ws.sorted, ws.n_keep, d_feats, ws.den, B, H, W, Hm, Wm, cap, top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid,
-        d_kpts_int);
+        d_kpts_int, (__half*)d_desc_split, split_rows);
   }
   XF_LAUNCH_CHECK();
   if (d_n_cand) XF_CUDA(cudaMemcpyAsync(d_n_cand, ws.n_cand, sizeof(int) * B, cudaMemcpyDeviceToDevice, st));

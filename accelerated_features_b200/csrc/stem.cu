@@ -159,6 +159,19 @@ struct Stem01W {
   float b1[8];
 };
 
+// Two fp32 FMAs per instruction (sm_100 FFMA2): d.xy = a.xy * b.xy + c.xy, each half an IEEE fma -- results are bit-identical to
+// two scalar fmaf calls.  The broadcast operand stays a scalar register and the weight pair comes from the constant bank through
+// the uniform datapath (LDCU), so the FMA-instruction count of the kernel halves.
+__device__ __forceinline__ float2 fma2(float a, float2 w, float2 c) {
+  float2 r;
+  const float2 aa = make_float2(a, a);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&aa)), "l"(*reinterpret_cast<const unsigned long long*>(&w)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return r;
+}
+
 __global__ void __launch_bounds__(128) stem01_kernel(const __grid_constant__ Stem01W P, const float* __restrict__ xn,
                                                      __half* __restrict__ out_split8, int H, int W) {
   const int Ho = H >> 1, Wo = W >> 1;
@@ -180,23 +193,27 @@ __global__ void __launch_bounds__(128) stem01_kernel(const __grid_constant__ Ste
       g[r][c] = (yin && x >= 0 && x < W) ? __ldg(row + x) : 0.f;
     }
   }
-  float acc[2][2][8];
+  float2 acc[2][2][4];   // [dy][dx][channel pair]
 #pragma unroll
-  for (int i = 0; i < 32; ++i) (&acc[0][0][0])[i] = 0.f;
+  for (int i = 0; i < 16; ++i) (&acc[0][0][0])[i] = make_float2(0.f, 0.f);
 #pragma unroll
   for (int r = 0; r < 5; ++r) {
     const int ay = 2 * oy0 - 1 + r;
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
       const int ax = 2 * ox0 - 1 + c;
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) a[ch] = fmaf(g[r + ky][c + kx], P.w0[(ky * 3 + kx) * 4 + ch], a[ch]);
+        for (int kx = 0; kx < 3; ++kx) {
+          const float gv = g[r + ky][c + kx];
+          const float* w = &P.w0[(ky * 3 + kx) * 4];
+          a2[0] = fma2(gv, make_float2(w[0], w[1]), a2[0]);
+          a2[1] = fma2(gv, make_float2(w[2], w[3]), a2[1]);
+        }
       const bool ain = ay >= 0 && ay < H && ax >= 0 && ax < W;   // outside the image block1.1 sees zero padding
+      float a[4] = {a2[0].x, a2[0].y, a2[1].x, a2[1].y};
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) a[ch] = ain ? fmaxf(a[ch] + P.b0[ch], 0.f) : 0.f;
 #pragma unroll
@@ -208,10 +225,11 @@ __global__ void __launch_bounds__(128) stem01_kernel(const __grid_constant__ Ste
           const int kx = c - 2 * dx;
           if (kx < 0 || kx > 2) continue;
 #pragma unroll
-          for (int ci = 0; ci < 4; ++ci)
+          for (int ci = 0; ci < 4; ++ci) {
+            const float* w = &P.w1[((ky * 3 + kx) * 4 + ci) * 8];
 #pragma unroll
-            for (int co = 0; co < 8; ++co)
-              acc[dy][dx][co] = fmaf(a[ci], P.w1[((ky * 3 + kx) * 4 + ci) * 8 + co], acc[dy][dx][co]);
+            for (int cp = 0; cp < 4; ++cp) acc[dy][dx][cp] = fma2(a[ci], make_float2(w[2 * cp], w[2 * cp + 1]), acc[dy][dx][cp]);
+          }
         }
       }
     }
@@ -224,7 +242,7 @@ __global__ void __launch_bounds__(128) stem01_kernel(const __grid_constant__ Ste
       uint32_t hw[4], lw[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float v0 = fmaxf(acc[dy][dx][2 * j] + P.b1[2 * j], 0.f), v1 = fmaxf(acc[dy][dx][2 * j + 1] + P.b1[2 * j + 1], 0.f);
+        const float v0 = fmaxf(acc[dy][dx][j].x + P.b1[2 * j], 0.f), v1 = fmaxf(acc[dy][dx][j].y + P.b1[2 * j + 1], 0.f);
         const __half2 h = __floats2half2_rn(v0, v1);
         const float2 hf = __half22float2(h);
         const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);

@@ -102,6 +102,25 @@ def estimate_pose_opencv(kpts0, kpts1, K0, K1, thresh, conf=0.99999):
     return ret
 
 
+def estimate_pose_gpu(kpts0, kpts1, K0, K1, thresh, iters: int = 2048, seed: int = 0):
+    """estimate_pose_poselib's role (megadepth1500.py:98-113) on the GPU: essential-matrix RANSAC (geometry.find_essential_batch,
+    8-point + Sampson + re-fit) and the cheirality test.  Same signature / return as estimate_pose_opencv."""
+    import torch
+    from .geometry import find_essential_batch, recover_pose
+    if len(kpts0) < 8:
+        return None
+    f = 0.25 * (K0[0, 0] + K0[1, 1] + K1[0, 0] + K1[1, 1])
+    n0 = ((kpts0 - K0[[0, 1], [2, 2]][None]) / K0[[0, 1], [0, 1]][None]).astype(np.float32)
+    n1 = ((kpts1 - K1[[0, 1], [2, 2]][None]) / K1[[0, 1], [0, 1]][None]).astype(np.float32)
+    E, mask, n_inl = find_essential_batch(torch.from_numpy(n0)[None].cuda(), torch.from_numpy(n1)[None].cuda(), None,
+                                          thr=thresh / f, iters=iters, seed=seed)
+    if int(n_inl.item()) < 8:
+        return None
+    m = mask[0].cpu().numpy()
+    R, t = recover_pose(E[0].double().cpu().numpy(), n0[m].astype(np.float64), n1[m].astype(np.float64))
+    return R, t, m
+
+
 def run_pose_benchmark(match_pairs, samples: Iterable[dict], ransac_thr: float = 2.5, batch_size: int = 64,
                        pose_fn=estimate_pose_opencv) -> dict:
     """run_pose_benchmark (megadepth1500.py:200-237) over batches.  `samples`: dicts with 'image0', 'image1' (H,W,3) uint8 BGR

@@ -219,10 +219,15 @@ class XFeat(torch.nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     # sparse path
     # ------------------------------------------------------------------------------------------------------------
-    def _detect_sparse_device(self, x, top_k: int, detection_threshold: float, div255=False):
+    @staticmethod
+    def _split_rows(top_k: int) -> int:
+        return (top_k + 511) // 512 * 512                       # row padding of the tensor-core matcher (mnn_tc.cu)
+
+    def _detect_sparse_device(self, x, top_k: int, detection_threshold: float, div255=False, want_split: bool = False):
         """Whole sparse extraction on the device, fixed-capacity outputs, no host sync.  `x` is one image batch or a list
         of batches of identical shape (they are normalised into one activation batch without concatenating the inputs);
         `div255` is one flag or one per batch (parse_input's "/255" applies to numpy inputs only, xfeat.py:400-401).
+        `want_split`: also return 'desc_split' (B, split_rows, 128) fp16, the matcher's pre-split operand rows.
         Returns dict of device tensors: keypoints (B,k,2), scores (B,k), descriptors (B,k,64), n_valid (B) int32."""
         xs = [self._to_bchw(t) for t in (x if isinstance(x, (list, tuple)) else [x])]
         flags = list(div255) if isinstance(div255, (list, tuple)) else [div255] * len(xs)
@@ -253,14 +258,17 @@ class XFeat(torch.nn.Module):
         if nbytes == 0:
             raise _lib.XFeatLibraryError("xfeat_sparse_workspace_bytes failed: " + self._lib.xfeat_last_error().decode())
         ws = self._workspace(nbytes)
+        split_rows = self._split_rows(top_k)
+        split = self._empty((B, split_rows, 128), torch.float16) if want_split else None
         with torch.cuda.device(self.dev):
-            _lib.check(self._lib.xfeat_detect_sparse(self._ctx, feats.data_ptr(), heat.data_ptr(), rel.data_ptr(), B, H, W,
-                                                     top_k, float(detection_threshold), float(_F32(rw)), float(_F32(rh)),
-                                                     kpts.data_ptr(), scores.data_ptr(), desc.data_ptr(),
-                                                     n_valid.data_ptr(), n_cand.data_ptr(), None, ws.data_ptr(),
-                                                     ws.numel(), self._stream()), "xfeat_detect_sparse")
+            _lib.check(self._lib.xfeat_detect_sparse_split(self._ctx, feats.data_ptr(), heat.data_ptr(), rel.data_ptr(), B, H, W,
+                                                           top_k, float(detection_threshold), float(_F32(rw)), float(_F32(rh)),
+                                                           kpts.data_ptr(), scores.data_ptr(), desc.data_ptr(),
+                                                           n_valid.data_ptr(), n_cand.data_ptr(), None, _ptr(split),
+                                                           split_rows if want_split else 0, ws.data_ptr(),
+                                                           ws.numel(), self._stream()), "xfeat_detect_sparse_split")
         return {"keypoints": kpts, "scores": scores, "descriptors": desc, "n_valid": n_valid, "n_cand": n_cand,
-                "feats": feats, "heat": heat, "reliability": rel, "H": H, "W": W}
+                "feats": feats, "heat": heat, "reliability": rel, "H": H, "W": W, "desc_split": split}
 
     @torch.inference_mode()
     def detectAndCompute(self, x, top_k=None, detection_threshold=None) -> List[Dict[str, torch.Tensor]]:
@@ -337,10 +345,15 @@ class XFeat(torch.nn.Module):
         if x2.shape[0] != B:
             raise RuntimeError("the two image sets must have the same batch size")
         if x1.shape[1:] == x2.shape[1:]:
-            o = self._detect_sparse_device([x1, x2], top_k, self.detection_threshold, [da, db])
+            presplit = self._lib.xfeat_get_mnn_impl() in (1, 3)     # the sampler writes the matcher's operand rows itself
+            o = self._detect_sparse_device([x1, x2], top_k, self.detection_threshold, [da, db], want_split=presplit)
             k1, k2 = o["keypoints"][:B], o["keypoints"][B:]
             d1, d2 = o["descriptors"][:B], o["descriptors"][B:]
             n1, n2 = o["n_valid"][:B], o["n_valid"][B:]
+            if presplit:
+                sp = o["desc_split"]
+                idx0, idx1, cnt = self._mnn_presplit_device(sp[:B], n1, sp[B:], n2, top_k, sp.shape[1], B, min_cossim)
+                return self._gather_matches(k1, k2, idx0, idx1, cnt, B, top_k)
         else:
             o1 = self._detect_sparse_device(x1, top_k, self.detection_threshold, da)
             o2 = self._detect_sparse_device(x2, top_k, self.detection_threshold, db)
@@ -348,12 +361,28 @@ class XFeat(torch.nn.Module):
                                       o1["n_valid"], o2["n_valid"])
         idx0, idx1, cnt = self._mnn_device(d1, n1, top_k, top_k * 64, d2, n2, top_k, top_k * 64, B, min_cossim,
                                            abs_bound=1.0)   # xfeat_detect_sparse writes unit-norm rows
+        return self._gather_matches(k1, k2, idx0, idx1, cnt, B, top_k)
+
+    def _gather_matches(self, k1, k2, idx0, idx1, cnt, B: int, top_k: int):
         mk0, mk1 = self._empty((B, top_k, 2)), self._empty((B, top_k, 2))
         with torch.cuda.device(self.dev):
             _lib.check(self._lib.xfeat_gather_matches(k1.data_ptr(), k2.data_ptr(), top_k, top_k, idx0.data_ptr(),
                                                       idx1.data_ptr(), cnt.data_ptr(), B, mk0.data_ptr(), mk1.data_ptr(),
                                                       self._stream()), "xfeat_gather_matches")
         return mk0, mk1, cnt
+
+    def _mnn_presplit_device(self, f1s, n1, f2s, n2, n_max: int, n_pad: int, batch: int, min_cossim: float):
+        """xfeat_mnn_match_presplit on the operand rows xfeat_detect_sparse_split wrote (no max-reduction / split pass)."""
+        idx0 = self._empty((batch, n_max), torch.int64)
+        idx1 = self._empty((batch, n_max), torch.int64)
+        cnt = self._empty((batch,), torch.int32)
+        ws = self._workspace(self._lib.xfeat_mnn_presplit_workspace_bytes(batch, n_max, n_max))
+        with torch.cuda.device(self.dev):
+            _lib.check(self._lib.xfeat_mnn_match_presplit(f1s.data_ptr(), _ptr(n1), n_max, f2s.data_ptr(), _ptr(n2), n_max, n_pad,
+                                                          batch, 13, float(min_cossim), idx0.data_ptr(), idx1.data_ptr(),
+                                                          cnt.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()),
+                       "xfeat_mnn_match_presplit")
+        return idx0, idx1, cnt
 
     @torch.inference_mode()
     def match_xfeat(self, img1, img2, top_k=None, min_cossim=-1) -> Tuple[np.ndarray, np.ndarray]:

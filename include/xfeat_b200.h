@@ -112,6 +112,16 @@ XF_API int xfeat_detect_sparse(xfeat_ctx* ctx, const float* d_feats, const float
                         float* d_kpts, float* d_scores, float* d_desc, int32_t* d_n_valid, int32_t* d_n_cand,
                         int32_t* d_kpts_int, void* d_ws, size_t ws_bytes, void* stream);
 
+/* xfeat_detect_sparse that ALSO writes the matcher's operand rows: d_desc_split (B, split_rows, 128) fp16 = [hi(64) | lo(64)] of
+ * descriptor * 2^13 (x = hi + lo; XF_DESC_SPLIT_SCALE_LOG2), rows past n_valid zero; split_rows a multiple of 512, >= top_k.
+ * xfeat_mnn_match_presplit consumes them, which removes the max-reduction and split passes of xfeat_mnn_match from the sparse
+ * path.  d_desc_split == NULL: identical to xfeat_detect_sparse. */
+#define XF_DESC_SPLIT_SCALE_LOG2 13
+XF_API int xfeat_detect_sparse_split(xfeat_ctx* ctx, const float* d_feats, const float* d_heat, const float* d_reliability,
+                              int B, int H, int W, int top_k, float threshold, float rw, float rh, float* d_kpts,
+                              float* d_scores, float* d_desc, int32_t* d_n_valid, int32_t* d_n_cand, int32_t* d_kpts_int,
+                              void* d_desc_split, int split_rows, void* d_ws, size_t ws_bytes, void* stream);
+
 XF_API size_t xfeat_dense_workspace_bytes(int B, int H, int W, int top_k);
 /* replaces: extractDense's topk over the reliability map + gathers + rescale (xfeat.py:366-375) and
  * extract_dualscale's "/s" (xfeat.py:388).  k = min(top_k, (H/8)*(W/8)).
@@ -153,6 +163,14 @@ XF_API int xfeat_mnn_match_bounded(const float* d_f1, const int32_t* d_n1, int n
                             const float* d_f2, const int32_t* d_n2, int n2_max, int64_t stride2,
                             int batch, float min_cossim, float abs_bound, int64_t* d_idx0, int64_t* d_idx1,
                             int32_t* d_n_matches, void* d_ws, size_t ws_bytes, void* stream);
+
+/* xfeat_mnn_match on operands the producer already split (xfeat_detect_sparse_split): d_f1s / d_f2s (batch, n_pad, 128) fp16 rows
+ * [hi(64) | lo(64)] of descriptor * 2^scale_log2.  Same outputs and tie rule as xfeat_mnn_match; implementations 1 and 3 only
+ * (XF_E_UNSUPPORTED otherwise). */
+XF_API size_t xfeat_mnn_presplit_workspace_bytes(int batch, int n1_max, int n2_max);
+XF_API int xfeat_mnn_match_presplit(const void* d_f1s, const int32_t* d_n1, int n1_max, const void* d_f2s, const int32_t* d_n2,
+                             int n2_max, int n_pad, int batch, int scale_log2, float min_cossim, int64_t* d_idx0,
+                             int64_t* d_idx1, int32_t* d_n_matches, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Gather matched keypoints: out0[b][m] = kpts0[b][idx0[b][m]], out1[b][m] = kpts1[b][idx1[b][m]] for m < n_matches[b]
  * (replaces the fancy-indexing at xfeat.py:186). kpts are (batch, n_max, 2) f32. */
@@ -220,6 +238,16 @@ XF_API size_t xfeat_ransac_workspace_bytes(int batch, int iters);
 XF_API int xfeat_ransac_homography(const float* d_pts0, const float* d_pts1, const int32_t* d_n, int n_max, int batch,
                                    float thr_px, int iters, uint32_t seed, float* d_H, uint8_t* d_inliers,
                                    int32_t* d_n_inliers, void* d_ws, size_t ws_bytes, void* stream);
+
+/* replaces: the relative-pose RANSAC the 1500-pair benchmarks run on the matches (poselib.estimate_relative_pose,
+ * modules/eval/megadepth1500.py:98-113): essential matrix from NORMALISED image coordinates d_x0 / d_x1 (batch, n_max, 2)
+ * (K^-1 applied by the caller), 8-point hypotheses projected onto the essential manifold, Sampson distance against `thr` (in
+ * normalised units: pixels / focal length), MSAC scoring, two least-squares re-fits.  Outputs d_E (batch, 9) row-major with
+ * x1^T E x0 = 0, d_inliers, d_n_inliers.  Fewer than 8 matches: zero matrix.  (The 8-point solver is degenerate for planar
+ * scenes, unlike poselib's 5-point solver.)  Workspace: xfeat_ransac_workspace_bytes. */
+XF_API int xfeat_ransac_essential(const float* d_x0, const float* d_x1, const int32_t* d_n, int n_max, int batch, float thr,
+                                  int iters, uint32_t seed, float* d_E, uint8_t* d_inliers, int32_t* d_n_inliers, void* d_ws,
+                                  size_t ws_bytes, void* stream);
 
 /* Test hook: run one folded conv layer of the packed table (index into csrc/layers.h) through the generic
  * kernels. in (B,Hi,Wi,Cin) NHWC -> out (B,Ho,Wo,Cout). */

@@ -223,3 +223,24 @@ def test_fast_equals_three_term_kernel(xf, assets_vga):
         assert torch.equal(res[1][2], res[4][2])
         for b, c in enumerate(res[1][2].tolist()):
             assert torch.equal(res[1][0][b, :c], res[4][0][b, :c]) and torch.equal(res[1][1][b, :c], res[4][1][b, :c])
+
+
+@pytest.mark.parametrize("impl", [1, 3])
+def test_presplit_operands_equal_split_pass(xf, assets_vga, impl):
+    """xfeat_detect_sparse_split writes the matcher's operand rows itself; xfeat_mnn_match_presplit on them must return exactly
+    what xfeat_mnn_match_bounded returns after its own split pass over the fp32 descriptors (ragged counts, B = 3)."""
+    ref, tgt = assets_vga
+    x = torch.from_numpy(np.stack([ref, tgt, ref[::-1].copy(), tgt, ref, tgt[:, ::-1].copy()])).permute(0, 3, 1, 2).float() / 255
+    with mnn_impl(xf, impl):
+        o = xf._detect_sparse_device(x, 3000, 0.05, want_split=True)
+        d, n, sp = o["descriptors"], o["n_valid"], o["desc_split"]
+        assert sp.shape == (6, 3072, 128) and sp.dtype == torch.float16
+        a = xf._mnn_device(d[:3], n[:3], 3000, 3000 * 64, d[3:], n[3:], 3000, 3000 * 64, 3, 0.5, abs_bound=1.0)
+        b = xf._mnn_presplit_device(sp[:3], n[:3], sp[3:], n[3:], 3000, 3072, 3, 0.5)
+    assert torch.equal(a[2], b[2])
+    for i, c in enumerate(a[2].tolist()):
+        assert torch.equal(a[0][i, :c], b[0][i, :c]) and torch.equal(a[1][i, :c], b[1][i, :c])
+    # the rows are hi + lo = descriptor * 2^13, zero past n_valid
+    nv = int(n[0])
+    rec = (sp[0, :nv, :64].float() + sp[0, :nv, 64:].float()) / 8192.0
+    assert (rec - d[0, :nv]).abs().max().item() < 1e-6 and float(sp[0, nv:].abs().sum()) == 0.0
