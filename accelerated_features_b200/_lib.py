@@ -22,6 +22,7 @@ SIGNATURES = {
     "xfeat_destroy": (None, [c_p]),
     "xfeat_resize_bilinear": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i64, c_i64, c_i64, c_i64, c_i, c_p, c_i, c_i, c_f, c_f, c_p]),
     "xfeat_preprocess": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i64, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_p, c_p, c_p]),
+    "xfeat_preprocess_scaled": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i64, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
     "xfeat_set_conv_impl": (None, [c_i]),
     "xfeat_set_halo_desc_mode": (None, [c_i]),
     "xfeat_get_conv_impl": (c_i, []),

@@ -225,8 +225,7 @@ extern "C" int xfeat_net(xfeat_ctx* ctx, const float* d_xn, int B, int H, int W,
     if (g_conv_impl == 2) {
       // fused head chains: activations stay in shared memory / TMEM between the 1x1 layers (head_chain_tc.cu)
       XF_RUN(launch_head_chain(ctx, 1, s8a, B, H8, W8, d_reliability, nullptr, st));                 // model.py:151
-      XF_RUN(launch_unfold8_split(d_xn, s8b, B, H8, W8, st));                                        // model.py:152
-      XF_RUN(launch_head_chain(ctx, 0, s8b, B, H8, W8, d_heat, d_kpt_logits, st));                   // + xfeat.py:242-247
+      XF_RUN(launch_head_chain(ctx, 0, d_xn, B, H8, W8, d_heat, d_kpt_logits, st));   // unfold8 (model.py:152) inside; + xfeat.py:242-247
       return XF_OK;
     }
     XF_RUN(launch_conv_tc(ctx, L_HH_0, s8a, B, H8, W8, s8b, nullptr, st));                          // model.py:151

@@ -29,6 +29,7 @@ struct HeadChainParams {
   float inv_ws_fin;
   int64_t npix;
   int Hc, Wc;             // cells per image (keypoint head: heat-map geometry)
+  const float* xn;        // keypoint head: normalised gray image (B, 8Hc, 8Wc); the 8x8 unfold + split happens in the kernel
   float* out;             // heat (B, 8Hc, 8Wc) or reliability (npix)
   float* logits;          // optional (npix, 65) raw logits (tests)
 };
@@ -60,10 +61,10 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
   for (int i = threadIdx.x; i < NH * 64; i += HC_THREADS) sBias[i] = __ldg(P.bias[i / 64] + (i & 63));
   for (int i = threadIdx.x; i < NF; i += HC_THREADS) sBias[NH * 64 + i] = (i < (MODE == 0 ? 65 : 1)) ? __ldg(P.bias_fin + i) : 0.f;
   if (warp == 0 && lane == 0) {
-    tc::tma_prefetch_desc(&P.amap);
+    if constexpr (MODE == 1) tc::tma_prefetch_desc(&P.amap);
     tc::mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&a_full[i], 1);
+      tc::mbar_init(&a_full[i], MODE == 0 ? 4 : 1);   // MODE 0: the slot's four epilogue warps write the layer-0 operand
       tc::mbar_init(&a_free[i], 1);
       tc::mbar_init(&acc_full[i], 1);
       tc::mbar_init(&a_ready[i], 4);
@@ -85,13 +86,15 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
       for (int l = 0; l < NH; ++l)
         for (int g = 0; g < 2; ++g) tc::tma_load_2d(sW + (size_t)(l * 2 + g) * HC_WBOX, &P.wmap[l], w_full, 0, g * 64);
       for (int g = 0; g < 2; ++g) tc::tma_load_2d(sWf + (size_t)g * WF_GROUP, &P.wfin, w_full, 0, g * NF);
-      uint32_t tcount = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        const int s = tcount & 1;
-        tc::mbar_wait(&a_free[s], ((tcount >> 1) & 1) ^ 1);
-        tc::mbar_expect_tx(&a_full[s], 2 * HC_ABOX);
-        tc::tma_load_2d(sA + (size_t)s * 2 * HC_ABOX, &P.amap, &a_full[s], 0, tile * 128);              // hi
-        tc::tma_load_2d(sA + (size_t)s * 2 * HC_ABOX + HC_ABOX, &P.amap, &a_full[s], 64, tile * 128);   // lo
+      if constexpr (MODE == 1) {   // (MODE 0: the epilogue warps build the layer-0 operand from the gray image themselves)
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+          const int s = tcount & 1;
+          tc::mbar_wait(&a_free[s], ((tcount >> 1) & 1) ^ 1);
+          tc::mbar_expect_tx(&a_full[s], 2 * HC_ABOX);
+          tc::tma_load_2d(sA + (size_t)s * 2 * HC_ABOX, &P.amap, &a_full[s], 0, tile * 128);              // hi
+          tc::tma_load_2d(sA + (size_t)s * 2 * HC_ABOX + HC_ABOX, &P.amap, &a_full[s], 64, tile * 128);   // lo
+        }
       }
     }
     __syncwarp();
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
       uint32_t g[2] = {0, 0};
       for (int i0 = 0; i0 < my_tiles; i0 += 2) {
         const int ns = (i0 + 1 < my_tiles) ? 2 : 1;
-        for (int s = 0; s < ns; ++s) tc::mbar_wait(&a_full[s], ((i0 >> 1)) & 1);
+        for (int s = 0; s < ns; ++s) tc::mbar_wait(&a_full[s], ((i0 >> 1)) & 1);   // layer-0 operand in smem (TMA, or the epilogue group)
         for (int l = 0; l <= NH; ++l) {
           for (int s = 0; s < ns; g[s] += 1, ++s) {
             const uint32_t a_addr = tc::smem_u32(sA + (size_t)s * 2 * HC_ABOX);
@@ -143,6 +146,49 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
     uint32_t gcount = 0;   // GEMMs of this slot consumed so far
     for (int i0 = 0; i0 < my_tiles; i0 += 2) {
       if (i0 + s >= my_tiles) break;
+     if constexpr (MODE == 0) {
+       // ---- layer-0 operand: XFeatModel._unfold2d(x, 8) (model.py:113-120) + split, straight from the normalised gray image:
+       // channel 8i+j of cell (h, w) = xn[8h+i, 8w+j].  The slot's previous tile has been fully consumed: its last GEMM completed
+       // before this group saw acc_full for it, and the group finished that tile's soft-max before coming here. ----
+       const int tile = (int)blockIdx.x + (i0 + s) * (int)gridDim.x;
+       unsigned char* a_hi = sA + (size_t)s * 2 * HC_ABOX;
+       unsigned char* a_lo = a_hi + HC_ABOX;
+       const int64_t cell = (int64_t)tile * 128 + r;
+       if (cell < P.npix) {
+         const int64_t b = cell / ((int64_t)P.Hc * P.Wc);
+         const int rem = (int)(cell - b * P.Hc * P.Wc);
+         const int h = rem / P.Wc, wc = rem - h * P.Wc;
+         const float* xp = P.xn + ((int64_t)b * P.Hc * 8 + (int64_t)h * 8) * (P.Wc * 8) + wc * 8;
+#pragma unroll
+         for (int i = 0; i < 8; ++i) {
+           const float4 a = __ldg(reinterpret_cast<const float4*>(xp + (int64_t)i * (P.Wc * 8)));
+           const float4 c = __ldg(reinterpret_cast<const float4*>(xp + (int64_t)i * (P.Wc * 8)) + 1);
+           const float x[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+           uint32_t hw[4], lw[4];
+#pragma unroll
+           for (int j = 0; j < 4; ++j) {
+             const __half2 hh = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+             const float2 hf = __half22float2(hh);
+             const __half2 lo = __floats2half2_rn(x[2 * j] - hf.x, x[2 * j + 1] - hf.y);
+             hw[j] = *reinterpret_cast<const uint32_t*>(&hh);
+             lw[j] = *reinterpret_cast<const uint32_t*>(&lo);
+           }
+           const int off = r * 128 + ((i ^ (r & 7)) << 4);      // 16-byte chunk i (channels 8i..8i+7) of row r, 128B swizzle
+           *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+           *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+         }
+       } else {
+#pragma unroll
+         for (int i = 0; i < 8; ++i) {
+           const int off = r * 128 + ((i ^ (r & 7)) << 4);
+           *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(0u, 0u, 0u, 0u);
+           *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(0u, 0u, 0u, 0u);
+         }
+       }
+       tc::fence_proxy_async();
+       __syncwarp();
+       if (lane == 0) tc::mbar_arrive(&a_full[s]);   // its own barrier: "input written" may run a phase ahead of a_ready's consumer
+     }
      for (int l = 0; l <= NH; ++l) {
       {
         const int tile = (int)blockIdx.x + (i0 + s) * (int)gridDim.x;
@@ -227,10 +273,11 @@ __global__ void __launch_bounds__(HC_THREADS, 1) head_chain_kernel(const __grid_
             const int Wf = P.Wc * 8;
             float* hp = P.out + ((int64_t)b * P.Hc * 8 + h * 8) * Wf + w * 8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {   // channel 8i+j -> pixel (8h+i, 8w+j)
-              float4* rp = reinterpret_cast<float4*>(hp + (int64_t)i * Wf);
-              rp[0] = make_float4(z[8 * i] * rs, z[8 * i + 1] * rs, z[8 * i + 2] * rs, z[8 * i + 3] * rs);
-              rp[1] = make_float4(z[8 * i + 4] * rs, z[8 * i + 5] * rs, z[8 * i + 6] * rs, z[8 * i + 7] * rs);
+            for (int i = 0; i < 8; ++i) {   // channel 8i+j -> pixel (8h+i, 8w+j): one 32-byte row piece per store
+              uint32_t v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(z[8 * i + j] * rs);
+              tc::st_global_v8(hp + (int64_t)i * Wf, v);
             }
           }
         } else {
@@ -281,8 +328,10 @@ static int make_w_map(CUtensorMap* m, const __half* ptr, int rows_per_group) {
 
 // mode 0: keypoint head on the unfolded split image (npix = B*Hc*Wc cells) -> heat (B,8Hc,8Wc) [+ logits];
 // mode 1: reliability head on the split feature map -> reliability (npix)
-int launch_head_chain(const xfeat_ctx* ctx, int mode, const __half* in_split, int B, int Hc, int Wc, float* out, float* logits,
+int launch_head_chain(const xfeat_ctx* ctx, int mode, const void* in, int B, int Hc, int Wc, float* out, float* logits,
                       cudaStream_t st) {
+  // mode 0: `in` = normalised gray image (B, 8Hc, 8Wc) fp32; mode 1: `in` = split feature map (npix, 128 halves)
+  const __half* in_split = (mode == 1) ? (const __half*)in : nullptr;
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -294,12 +343,17 @@ int launch_head_chain(const xfeat_ctx* ctx, int mode, const __half* in_split, in
   const cuuint64_t strides[1] = {256};
   const cuuint32_t box[2] = {64, 128};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&P.amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)in_split, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(head chain input) failed: %d", (int)r);
-    return XF_E_CUDA;
+  if (mode == 1) {
+    CUresult r = enc(&P.amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)in_split, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(head chain input) failed: %d", (int)r);
+      return XF_E_CUDA;
+    }
+  } else {
+    memset(&P.amap, 0, sizeof(P.amap));
   }
+  P.xn = (mode == 0) ? (const float*)in : nullptr;
   const int hidden0 = (mode == 0) ? L_KH_0 : L_HH_0, nh = (mode == 0) ? 3 : 2, lfin = (mode == 0) ? L_KH_3 : L_HH_2;
   int rc;
   for (int l = 0; l < nh; ++l) {

@@ -285,6 +285,231 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_kernel(const __grid_cons
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent form of mnn_tc_kernel (round 2): one CTA per SM walks work items (pair, direction, 256-row block) instead of one
+// CTA per item, so barrier initialisation, the TMEM allocation and -- above all -- the 64 KB A-slab load of the NEXT item overlap
+// the tiles of the current one (A slabs double buffered, 2-stage ring of B tiles).  13.8 waves of one-shot CTAs paid the
+// prologue and the drain 14 times; here they are paid once.  Same arithmetic, same epilogue, same results.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TCP_NSB = 2;   // (three stages would need 232.7 KB: 256 bytes over the per-CTA maximum)
+constexpr size_t TCP_SMEM = 1024 + (size_t)(8 + 2 * TCP_NSB) * TC_BOX_BYTES + 256 + 2 * 128 * 8;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) mnn_tc_persist_kernel(const __grid_constant__ TcMaps maps,
+                                                                       const int* __restrict__ n1p, int n1_max,
+                                                                       const int* __restrict__ n2p, int n2_max, int n_pad, int batch,
+                                                                       unsigned long long* __restrict__ best12,
+                                                                       unsigned long long* __restrict__ best21) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = base;                       // [buffer 2][slab 2][hi, lo] boxes
+  unsigned char* sB = base + 8 * TC_BOX_BYTES;    // [stage TCP_NSB][hi, lo] boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (8 + 2 * TCP_NSB) * TC_BOX_BYTES);
+  uint64_t* a_full = bars;                        // [2]
+  uint64_t* a_empty = bars + 2;                   // [2]
+  uint64_t* b_full = bars + 4;                    // [TCP_NSB]
+  uint64_t* b_empty = b_full + TCP_NSB;           // [TCP_NSB]
+  uint64_t* acc_full = b_empty + TCP_NSB;         // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  unsigned long long* sMerge = reinterpret_cast<unsigned long long*>(base + (8 + 2 * TCP_NSB) * TC_BOX_BYTES + 256);   // [2 slabs][128 rows]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int RB = n_pad / TC_ROWS;
+  const int n_items = batch * 2 * RB;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&maps.m1);
+    tc::tma_prefetch_desc(&maps.m2);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&a_full[i], 1);
+      tc::mbar_init(&a_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 8);
+    }
+    for (int i = 0; i < TCP_NSB; ++i) {
+      tc::mbar_init(&b_full[i], 1);
+      tc::mbar_init(&b_empty[i], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // item -> (pair, dir, row block); every role walks the same sequence and skips the same (empty) items
+  auto decode = [&](int item, int& pair, int& dir, int& row0, int& n_rows, int& n_cols) {
+    const int rb = item % RB, pd = item / RB;
+    pair = pd >> 1;
+    dir = pd & 1;
+    row0 = rb * TC_ROWS;
+    const int n1 = n1p ? min(__ldg(n1p + pair), n1_max) : n1_max;
+    const int n2 = n2p ? min(__ldg(n2p + pair), n2_max) : n2_max;
+    n_rows = dir ? n2 : n1;
+    n_cols = dir ? n1 : n2;
+    return row0 < n_rows && n_cols > 0;
+  };
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      uint32_t ai = 0, bi = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int pair, dir, row0, n_rows, n_cols;
+        if (!decode(item, pair, dir, row0, n_rows, n_cols)) continue;
+        const CUtensorMap* mapA = dir ? &maps.m2 : &maps.m1;
+        const CUtensorMap* mapB = dir ? &maps.m1 : &maps.m2;
+        const int T = (n_cols + TC_BN - 1) / TC_BN;
+        const int ab = ai & 1;
+        tc::mbar_wait(&a_empty[ab], ((ai >> 1) & 1) ^ 1);
+        tc::mbar_expect_tx(&a_full[ab], 4 * TC_BOX_BYTES);
+        const int arow = pair * n_pad + row0;
+        for (int slab = 0; slab < 2; ++slab)
+          for (int kb = 0; kb < 2; ++kb)
+            tc::tma_load_2d(sA + ((ab * 2 + slab) * 2 + kb) * TC_BOX_BYTES, mapA, &a_full[ab], kb * 64, arow + slab * 128);
+        ++ai;
+        const int brow = pair * n_pad;
+        for (int t = 0; t < T; ++t, ++bi) {
+          const int s = bi % TCP_NSB;
+          tc::mbar_wait(&b_empty[s], ((bi / TCP_NSB) & 1) ^ 1);
+          tc::mbar_expect_tx(&b_full[s], 2 * TC_BOX_BYTES);
+          for (int kb = 0; kb < 2; ++kb)
+            tc::tma_load_2d(sB + (s * 2 + kb) * TC_BOX_BYTES, mapB, &b_full[s], kb * 64, brow + t * TC_BN);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc(/*F16*/ 0, 128, TC_BN);
+      uint32_t ai = 0, bi = 0, tt = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int pair, dir, row0, n_rows, n_cols;
+        if (!decode(item, pair, dir, row0, n_rows, n_cols)) continue;
+        const int T = (n_cols + TC_BN - 1) / TC_BN;
+        const int ab = ai & 1;
+        // K-block order hi.hi, then (dir ? lo.hi, hi.lo : hi.lo, lo.hi): S12[i][j] == S21[j][i] bit for bit (see mnn_tc_kernel)
+        const int a_sel[3] = {0, dir ? 1 : 0, dir ? 0 : 1};
+        const int b_sel[3] = {0, dir ? 0 : 1, dir ? 1 : 0};
+        tc::mbar_wait(&a_full[ab], (ai >> 1) & 1);
+        for (int t = 0; t < T; ++t, ++bi, ++tt) {
+          const int s = bi % TCP_NSB, as = tt & 1;
+          tc::mbar_wait(&b_full[s], (bi / TCP_NSB) & 1);
+          tc::mbar_wait(&acc_empty[as], ((tt >> 1) & 1) ^ 1);
+          tc::tc_fence_after();
+#pragma unroll
+          for (int slab = 0; slab < 2; ++slab) {
+            const uint32_t d = tmem + as * 256 + slab * 128;
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) {
+              const uint64_t da = tc::make_desc_sw128(tc::smem_u32(sA + ((ab * 2 + slab) * 2 + a_sel[kb]) * TC_BOX_BYTES), 1024);
+              const uint64_t db = tc::make_desc_sw128(tc::smem_u32(sB + (s * 2 + b_sel[kb]) * TC_BOX_BYTES), 1024);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) tc::umma_f16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            }
+          }
+          tc::umma_commit(&b_empty[s]);
+          tc::umma_commit(&acc_full[as]);
+        }
+        tc::umma_commit(&a_empty[ab]);
+        ++ai;
+      }
+    }
+    __syncwarp();
+  } else {
+    // epilogue: as mnn_tc_kernel (TMEM lane quarter q, column half hc), state reset per item
+    const int q = warp & 3, hc = (warp - 2) >> 2;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t tt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int pair, dir, row0, n_rows, n_cols;
+      if (!decode(item, pair, dir, row0, n_rows, n_cols)) continue;
+      const int T = (n_cols + TC_BN - 1) / TC_BN;
+      float best[2] = {-INFINITY, -INFINITY};
+      uint32_t bidx[2] = {0xffffffffu, 0xffffffffu};
+      auto reduce_chunk = [&](const uint32_t (&r)[32], int col0, int slab) {
+        if (col0 + 32 <= n_cols) {
+          float m = __uint_as_float(r[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+          if (m > best[slab]) {            // strict: earlier columns win ties (torch.max / argmax rule)
+            int j0 = 31;
+#pragma unroll
+            for (int j = 30; j >= 0; --j)
+              if (__uint_as_float(r[j]) == m) j0 = j;
+            best[slab] = m;
+            bidx[slab] = (uint32_t)(col0 + j0);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(r[j]);
+            if (col0 + j < n_cols && v > best[slab]) { best[slab] = v; bidx[slab] = (uint32_t)(col0 + j); }
+          }
+        }
+      };
+      for (int t = 0; t < T; ++t, ++tt) {
+        const int as = tt & 1;
+        tc::mbar_wait(&acc_full[as], (tt >> 1) & 1);
+        tc::tc_fence_after();
+        uint32_t ra[32], rb[32];
+        const uint32_t tb = lane_addr + as * 256 + hc * 64;
+        const int cb = t * TC_BN + hc * 64;
+        __syncwarp();
+        tc::tmem_ld_32x32(tb, ra);
+        tc::tmem_ld_wait();
+        __syncwarp();
+        tc::tmem_ld_32x32(tb + 32, rb);
+        reduce_chunk(ra, cb, 0);
+        tc::tmem_ld_wait();
+        __syncwarp();
+        tc::tmem_ld_32x32(tb + 128, ra);
+        reduce_chunk(rb, cb + 32, 0);
+        tc::tmem_ld_wait();
+        __syncwarp();
+        tc::tmem_ld_32x32(tb + 128 + 32, rb);
+        reduce_chunk(ra, cb, 1);
+        tc::tmem_ld_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&acc_empty[as]);
+        reduce_chunk(rb, cb + 32, 1);
+      }
+      // merge the two column halves of every row (lower column index wins ties through the packed compare)
+      unsigned long long pk[2];
+#pragma unroll
+      for (int slab = 0; slab < 2; ++slab) pk[slab] = (bidx[slab] == 0xffffffffu) ? 0ull : pack_vi(best[slab], bidx[slab]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // the previous item's merge reads are complete
+      if (hc == 1) {
+        sMerge[0 * 128 + q * 32 + lane] = pk[0];
+        sMerge[1 * 128 + q * 32 + lane] = pk[1];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // epilogue warps only
+      if (hc == 0) {
+        unsigned long long* out = dir ? best21 : best12;
+        const int out_stride = dir ? n2_max : n1_max;
+#pragma unroll
+        for (int slab = 0; slab < 2; ++slab) {
+          const unsigned long long o = sMerge[slab * 128 + q * 32 + lane];
+          const unsigned long long m = o > pk[slab] ? o : pk[slab];
+          const int row = row0 + slab * 128 + q * 32 + lane;
+          if (row < n_rows) out[(int64_t)pair * out_stride + row] = m;
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Single-pass variant (default): S is computed ONCE; the same accumulator tile yields the running row arg-max (as above) and
 // the column arg-max.  A thread owns a row, so a column maximum is a reduction across the 32 lanes of a warp:
@@ -757,6 +982,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   }
 }
 
+
+// Both directions of the three-term scan over the full sets: the persistent kernel (default), or one CTA per (row block, pair,
+// direction) with XFEAT_MNN_ONESHOT=1 (A/B measurements).
+static int launch_mnn_tc_main(const TcMaps& maps, const int* n1, int n1_max, const int* n2, int n2_max, int n_pad, int batch,
+                              unsigned long long* best12, unsigned long long* best21, cudaStream_t st) {
+  static const bool oneshot = getenv("XFEAT_MNN_ONESHOT") != nullptr;
+  if (oneshot) {
+    XF_DYN_SMEM(mnn_tc_kernel, TC_SMEM);
+    dim3 grid(n_pad / TC_ROWS, batch, 2);
+    TcMaps4 m4;
+    m4.a0 = maps.m1; m4.b0 = maps.m2; m4.a1 = maps.m2; m4.b1 = maps.m1;
+    mnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(m4, n1, n1_max, n2, n2_max, n_pad, best12, best21, nullptr, nullptr);
+    XF_LAUNCH_CHECK();
+    return XF_OK;
+  }
+  int dev = 0, sms = 148;
+  XF_CUDA(cudaGetDevice(&dev));
+  XF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  XF_DYN_SMEM(mnn_tc_persist_kernel, TCP_SMEM);
+  const int n_items = batch * 2 * (n_pad / TC_ROWS);
+  mnn_tc_persist_kernel<<<n_items < sms ? n_items : sms, TC_THREADS, TCP_SMEM, st>>>(maps, n1, n1_max, n2, n2_max, n_pad, batch, best12,
+                                                                                    best21);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
+}
+
 struct MnnTcWs {
   __half *f1s, *f2s;
   unsigned long long *best12, *best21;
@@ -850,12 +1101,7 @@ int launch_mnn_tc(const float* f1, const int* n1, int n1_max, int64_t stride1, c
     XF_LAUNCH_CHECK();
     return XF_OK;
   }
-  dim3 grid(n_pad / TC_ROWS, batch, 2);
-  TcMaps4 m4;
-  m4.a0 = maps.m1; m4.b0 = maps.m2; m4.a1 = maps.m2; m4.b1 = maps.m1;
-  mnn_tc_kernel<<<grid, TC_THREADS, TC_SMEM, st>>>(m4, n1, n1_max, n2, n2_max, n_pad, ws.best12, ws.best21, nullptr, nullptr);
-  XF_LAUNCH_CHECK();
-  return XF_OK;
+  return launch_mnn_tc_main(maps, n1, n1_max, n2, n2_max, n_pad, batch, ws.best12, ws.best21, st);
 }
 
 int launch_mnn_tc_rows(const __half* a0, const __half* b0, const __half* a1, const __half* b1, const int* n1, int n1_max,
@@ -893,7 +1139,11 @@ int launch_mnn_tc_presplit(const __half* f1s, const int* n1, int n1_max, const _
     XF_LAUNCH_CHECK();
     return XF_OK;
   }
-  return launch_mnn_tc_rows(f1s, f2s, f2s, f1s, n1, n1_max, n2, n2_max, n_pad, batch, nullptr, nullptr, b12, b21, st);
+  TcMaps maps;
+  int rc;
+  if ((rc = make_map(&maps.m1, f1s, (uint64_t)batch * n_pad))) return rc;
+  if ((rc = make_map(&maps.m2, f2s, (uint64_t)batch * n_pad))) return rc;
+  return launch_mnn_tc_main(maps, n1, n1_max, n2, n2_max, n_pad, batch, b12, b21, st);
 }
 
 int launch_absmax(const float* f, const int* np, int n_max, int64_t stride, int batch, unsigned* out, cudaStream_t st) {

@@ -255,14 +255,20 @@ extern "C" int xfeat_resize_bilinear(const void* d_in, int dtype, int B, int C, 
 extern "C" int xfeat_preprocess(const void* d_img, int dtype, int B, int C, int Hi, int Wi, int64_t stride_b,
                                 int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255, int H, int W,
                                 float* d_xn, double* d_stats, void* stream) {
+  // ATen area_pixel_compute_scale (size given): scale = float(in) / out
+  return xfeat_preprocess_scaled(d_img, dtype, B, C, Hi, Wi, stride_b, stride_c, stride_h, stride_w, div255, H, W,
+                                 (float)Hi / (float)H, (float)Wi / (float)W, d_xn, d_stats, stream);
+}
+
+extern "C" int xfeat_preprocess_scaled(const void* d_img, int dtype, int B, int C, int Hi, int Wi, int64_t stride_b,
+                                       int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255, int H, int W,
+                                       float sh, float sw, float* d_xn, double* d_stats, void* stream) {
   XF_REQUIRE(d_img && d_xn && d_stats, "preprocess: null pointer");
   XF_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hi > 0 && Wi > 0, "preprocess: bad shape");
   XF_REQUIRE(H > 0 && W > 0 && (H % 32) == 0 && (W % 32) == 0, "preprocess: H, W must be positive multiples of 32");
   XF_REQUIRE(dtype == XF_DTYPE_F32 || dtype == XF_DTYPE_U8, "preprocess: unsupported dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
   XF_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * 2 * B, st));
-  // ATen area_pixel_compute_scale (size given): scale = float(in) / out
-  const float sh = (float)Hi / (float)H, sw = (float)Wi / (float)W;
   dim3 grid(xf::cdiv(W, 64), xf::cdiv(H, 4), B);
   const bool fast = dtype == XF_DTYPE_F32 && Hi == H && Wi == W && stride_w == 1 && ((uintptr_t)d_img % 16) == 0 &&
                     stride_b % 4 == 0 && stride_c % 4 == 0 && stride_h % 4 == 0;

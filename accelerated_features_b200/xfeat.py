@@ -178,16 +178,24 @@ class XFeat(torch.nn.Module):
                 f"{what}: NMS candidate buffer overflow (more than H*W/4 maxima above the threshold) for batch items {bad}; "
                 "nothing is returned for them rather than an arbitrary subset")
 
-    def _preprocess(self, x: torch.Tensor, H: int, W: int, div255: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """xfeat_preprocess: resize to (H,W), channel mean, InstanceNorm -> (B,H,W) fp32 (optionally into `out`)."""
+    def _preprocess(self, x: torch.Tensor, H: int, W: int, div255: bool, out: Optional[torch.Tensor] = None,
+                    scale: Optional[float] = None) -> torch.Tensor:
+        """xfeat_preprocess: resize to (H,W), channel mean, InstanceNorm -> (B,H,W) fp32 (optionally into `out`).
+        `scale`: source-coordinate scale of an F.interpolate(scale_factor=1/scale) (default: in / out, F.interpolate(size=...))."""
         x, code = self._img_args(x)
         B, C, Hi, Wi = x.shape
         sb, sc, sh, sw = x.stride()
         xn = self._empty((B, H, W)) if out is None else out
         stats = self._empty((B, 2), torch.float64)
         with torch.cuda.device(self.dev):
-            _lib.check(self._lib.xfeat_preprocess(x.data_ptr(), code, B, C, Hi, Wi, sb, sc, sh, sw, int(div255), H, W,
-                                                  xn.data_ptr(), stats.data_ptr(), self._stream()), "xfeat_preprocess")
+            if scale is None:
+                _lib.check(self._lib.xfeat_preprocess(x.data_ptr(), code, B, C, Hi, Wi, sb, sc, sh, sw, int(div255), H, W,
+                                                      xn.data_ptr(), stats.data_ptr(), self._stream()), "xfeat_preprocess")
+            else:
+                sf = float(_F32(scale))
+                _lib.check(self._lib.xfeat_preprocess_scaled(x.data_ptr(), code, B, C, Hi, Wi, sb, sc, sh, sw, int(div255), H, W, sf, sf,
+                                                             xn.data_ptr(), stats.data_ptr(), self._stream()),
+                           "xfeat_preprocess_scaled")
         return xn
 
     def _run_net(self, xn: torch.Tensor, B: int, H: int, W: int, want_logits: bool = False):
@@ -557,14 +565,18 @@ class XFeat(torch.nn.Module):
     # semi-dense path
     # ------------------------------------------------------------------------------------------------------------
     def _extract_dense_into(self, x: torch.Tensor, div255: bool, top_k: int, div_scale: float, scale_value: float,
-                            out_rows: int, out_offset: int, kpts, desc, scales):
-        """extractDense (xfeat.py:356-377) writing k rows at `out_offset`; returns k."""
+                            out_rows: int, out_offset: int, kpts, desc, scales, pre_scale: Optional[float] = None):
+        """extractDense (xfeat.py:356-377) writing k rows at `out_offset`; returns k.  `pre_scale` = s: `x` is the ORIGINAL image and
+        extract_dualscale's F.interpolate(scale_factor=s) (xfeat.py:380-381) is folded into the gray conversion -- only used when
+        floor(H*s), floor(W*s) are multiples of 32, where preprocess_tensor's own resize is the identity."""
         B, _, Hi, Wi = x.shape
+        if pre_scale is not None:
+            Hi, Wi = int(math.floor(Hi * pre_scale)), int(math.floor(Wi * pre_scale))
         H, W = (Hi // 32) * 32, (Wi // 32) * 32
         if H == 0 or W == 0:
             raise RuntimeError("image smaller than 32 pixels")
         rh, rw = Hi / H, Wi / W
-        xn = self._preprocess(x, H, W, div255)
+        xn = self._preprocess(x, H, W, div255, scale=None if pre_scale is None else 1.0 / pre_scale)
         feats, _, rel, _ = self._run_net(xn, B, H, W)
         cells = (H // 8) * (W // 8)
         k = min(cells, top_k)
@@ -611,11 +623,15 @@ class XFeat(torch.nn.Module):
             k2 = min(self._cells_of(int(math.floor(Hi * s2)), int(math.floor(Wi * s2))), t2)
             K = k1 + k2
             kpts, desc, scales = self._empty((B, K, 2)), self._empty((B, K, 64)), self._empty((B, K))
-            x1 = self._resize_scale(x, div255, s1)
-            self._extract_dense_into(x1, False, k1, s1, 1 / s1, K, 0, kpts, desc, scales)
-            del x1
-            x2 = self._resize_scale(x, div255, s2)
-            self._extract_dense_into(x2, False, k2, s2, 1 / s2, K, k1, kpts, desc, scales)
+            for s, k, off in ((s1, k1, 0), (s2, k2, k1)):
+                Hs, Ws = int(math.floor(Hi * s)), int(math.floor(Wi * s))
+                if Hs % 32 == 0 and Ws % 32 == 0:
+                    # the 3-channel resized image (1.6 GB per 64 x 1280x960 at s = 1.3) is never written: resize + gray in one pass
+                    self._extract_dense_into(x, div255, k, s, 1 / s, K, off, kpts, desc, scales, pre_scale=s)
+                else:
+                    xs = self._resize_scale(x, div255, s)
+                    self._extract_dense_into(xs, False, k, s, 1 / s, K, off, kpts, desc, scales)
+                    del xs
         else:
             K = min(self._cells_of(Hi, Wi), self._unlimited(top_k))
             kpts, desc, scales = self._empty((B, K, 2)), self._empty((B, K, 64)), self._empty((B, K))

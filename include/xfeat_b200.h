@@ -84,6 +84,15 @@ XF_API int xfeat_preprocess(const void* d_img, int dtype, int B, int C, int Hi, 
                      int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255,
                      int H, int W, float* d_xn, double* d_stats, void* stream);
 
+/* xfeat_preprocess with explicit source-coordinate scales (src = (dst + 0.5) * scale - 0.5): F.interpolate(scale_factor = s) uses
+ * scale = float(1 / s) whatever floor(Hi * s) is (xfeat.py:380-381), F.interpolate(size = ...) uses in / out (xfeat.py:239).  With
+ * it extract_dualscale's resize (3 channels written and read back) folds into the gray conversion whenever the scaled size is
+ * already a multiple of 32 (then preprocess_tensor's own resize is the identity): per-channel interpolation in ATen's operation
+ * order, channel sum, division -- bit-identical to the two-step form. */
+XF_API int xfeat_preprocess_scaled(const void* d_img, int dtype, int B, int C, int Hi, int Wi,
+                            int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w, int div255,
+                            int H, int W, float scale_h, float scale_w, float* d_xn, double* d_stats, void* stream);
+
 /* Implementation switch of the conv layers inside xfeat_net (process-wide): 0 = fp32 CUDA-core kernels everywhere,
  * 1 = tcgen05 tensor-core kernels (split-fp16 operands, fp32 accumulation in TMEM), 2 = as 1 plus halo-patch operand
  * reuse for the 3x3 stride-1 layers.  xfeat_set_halo_desc_mode is a bring-up knob of mode 2 (1 = PTX base_offset rule). */

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Secondary BASELINE.json configs (not bench.py lines): C1 single-pair latency, C3 semi-dense 1280x960 throughput,
-C5 MNN sweep 2k..32k.  Writes one JSON document to stdout.   python tools/bench_configs.py > gpurun_out/configs.json"""
+"""Secondary BASELINE.json configs (not bench.py lines): C1 single-pair latency and the C5 MNN sweep 2k..32k (C3, the semi-dense
+1280x960 batch, is `bench.py --config star`).  Writes one JSON document to stdout.
+    python tools/bench_configs.py > gpurun_out/configs.json"""
 import json
 import os
 import sys
@@ -43,24 +44,14 @@ for _ in range(20):
 out["C1_single_vga_pair"] = {"ms_per_pair_wall": 1e3 * (time.perf_counter() - t0) / 20, "matches": int(len(mk0)),
                              "note": "asset pair resized to 640x480, numpy uint8 in -> numpy out, includes H2D/D2H and host sync"}
 
-# C3: semi-dense, 64 pairs of 1280x960 (device-resident inputs)
-gen = torch.Generator().manual_seed(0)
-x1 = torch.randn(64, 3, 960, 1280, generator=gen).cuda()
-x2 = torch.randn(64, 3, 960, 1280, generator=gen).cuda()
-ms = timed(lambda: xf._match_star_device(x1, x2, 4096), n=5, warm=2)
-out["C3_star_1280x960_b64"] = {"ms_per_step": ms, "pairs_per_s": 64 / (ms / 1e3), "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30,
-                               "algorithmic_gflop_per_pair": 46.3}
-del x1, x2
-torch.cuda.empty_cache()
-
-# C5: MNN sweep, unit-norm 64-D, both implementations
+# C5: MNN sweep, unit-norm 64-D: default (1: three-term split, persistent), 4 (fp16 filter + exact re-score), 0 (fp32 CUDA cores)
 sweep = []
 for n in (2048, 4096, 8192, 16384, 32768):
     gen = torch.Generator().manual_seed(n)
     f1 = F.normalize(torch.randn(n, 64, generator=gen), dim=-1).cuda()
     f2 = F.normalize(torch.randn(n, 64, generator=gen), dim=-1).cuda()
     row = {"n": n}
-    for impl, name in ((2, "tcgen05"), (1, "tcgen05_two_gemm"), (0, "fp32_simt")):
+    for impl, name in ((1, "tcgen05_three_term_default"), (4, "tcgen05_filter_plus_exact"), (0, "fp32_simt")):
         xf._lib.xfeat_set_mnn_impl(impl)
         ms = timed(lambda: xf._mnn_device(f1, None, n, 0, f2, None, n, 0, 1, -1), n=10, warm=3)
         flops = 2.0 * n * n * 64
@@ -71,7 +62,7 @@ for n in (2048, 4096, 8192, 16384, 32768):
     idx0, idx1, cnt = xf._mnn_device(f1, None, n, 0, f2, None, n, 0, 1, -1)
     row["mutual_matches"] = int(cnt.item())
     sweep.append(row)
-xf._lib.xfeat_set_mnn_impl(2)
+xf._lib.xfeat_set_mnn_impl(1)
 out["C5_mnn_sweep"] = {"rows": sweep, "note": "single pair per call (a 32k x 32k pair fills the GPU; small N under-fills 148 SMs); "
                        "reference-equivalent GB/s = bytes the reference's materialised S (written + read) would move / our time; "
                        f"HBM copy peak {peaks['hbm_gbs']} GB/s"}

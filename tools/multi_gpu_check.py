@@ -50,6 +50,21 @@ def cnt_dummy(d):
 
 
 star = par.star_image_sharded(extract, match_refine, s1, s2)
+# time it once more (warm) and say what crossed NVLink: every rank all-gathers the coarse blocks of its 2B/world images
+torch.cuda.synchronize(); dist.barrier()
+t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+t0.record()
+par.star_image_sharded(extract, match_refine, s1, s2)
+t1.record()
+torch.cuda.synchronize()
+ms = torch.tensor([t0.elapsed_time(t1)], device="cuda")
+dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+if rank == 0:
+    kk = int(2048 * 0.2) + int(2048 * 0.8)
+    bytes_per_image = kk * (64 + 2 + 1) * 4
+    recv = (2 * B - 2 * B // world) * bytes_per_image
+    print(f"[rank0] star image-sharded x{world}: {float(ms):.2f} ms (max over ranks); all-gather of {2 * B} coarse blocks x {bytes_per_image / 1e6:.2f} MB "
+          f"= {recv / 1e6:.2f} MB received per rank over NVLink")
 if rank == 0:
     ref = xf.match_xfeat_star(s1, s2, top_k=2048)
     same = len(star) == B and all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(star, ref))
