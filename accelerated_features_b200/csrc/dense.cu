@@ -103,11 +103,16 @@ extern "C" int xfeat_detect_dense(xfeat_ctx* ctx, const float* d_feats, const fl
   const int64_t total = (int64_t)B * cells;
   xf::dense_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_reliability, cells, total, ws.keys);
   XF_LAUNCH_CHECK();
-  xf::uniform_offsets_kernel<<<xf::cdiv(B, 128), 128, 0, st>>>(cells, B, ws.seg_begin, ws.seg_end);
-  XF_LAUNCH_CHECK();
-  size_t tb = ws.cub_bytes;
-  XF_CUDA(cub::DeviceSegmentedSort::SortKeysDescending(ws.cub_temp, tb, ws.keys, ws.sorted, (int)total, B, ws.seg_begin,
-                                                       ws.seg_end, st));
+  static const bool force_cub = getenv("XFEAT_TOPK_CUB") != nullptr;
+  if (!force_cub && k <= 8192) {   // radix select + sort of the k survivors per image (sparse.cu) instead of sorting every cell
+    if ((rc = xf::launch_topk_select_sort(ws.keys, nullptr, cells, cells, k, B, ws.sorted, st))) return rc;
+  } else {
+    xf::uniform_offsets_kernel<<<xf::cdiv(B, 128), 128, 0, st>>>(cells, B, ws.seg_begin, ws.seg_end);
+    XF_LAUNCH_CHECK();
+    size_t tb = ws.cub_bytes;
+    XF_CUDA(cub::DeviceSegmentedSort::SortKeysDescending(ws.cub_temp, tb, ws.keys, ws.sorted, (int)total, B, ws.seg_begin,
+                                                         ws.seg_end, st));
+  }
   const int64_t warps = (int64_t)B * k;
   xf::dense_gather_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
       ws.sorted, d_feats, B, cells, Wm, k, rw, rh, div_scale, scale_value, out_rows, out_offset, d_kpts, d_desc, d_scales,

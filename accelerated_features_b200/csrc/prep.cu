@@ -65,6 +65,77 @@ __global__ void __launch_bounds__(256) gray_resize_kernel(const void* __restrict
   }
 }
 
+// gray_resize_kernel for fp32 planes with unit pixel stride (the dual-scale star path resizes 64 x 3 x 960 x 1280 four times per
+// step): one thread owns 4 consecutive output columns x GRX_ROWS rows, so the 4 column taps are computed once and reused for every
+// row and channel, the 16 loads of a (row, channel) are issued together, offsets inside an image are 32-bit, the output is one
+// 128-bit store per row and the fp64 statistics take one atomic pair per 64 x 16 pixel block.  Per-pixel arithmetic is the
+// generic kernel's (ATen upsample_bilinear2d order), so the two produce identical bits.
+constexpr int GRX_ROWS = 4;
+__global__ void __launch_bounds__(256) gray_resize_f32x4_kernel(const float* __restrict__ img, int C, int Hi, int Wi, int64_t sb,
+                                                                int sc, int sh, int div255, int H, int W4, float scale_h,
+                                                                float scale_w, float* __restrict__ gray,
+                                                                double* __restrict__ stats) {
+  const int b = blockIdx.z;
+  const int x4 = blockIdx.x * 64 + (threadIdx.x & 63);
+  const bool in = x4 < W4;
+  const float* pb = img + (int64_t)b * sb;
+  LinTap tx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tx[j] = lin_tap(in ? 4 * x4 + j : 0, scale_w, Wi);
+  double s = 0.0, ss = 0.0;
+  const float fc = (float)C;
+#pragma unroll 1
+  for (int r = 0; r < GRX_ROWS; ++r) {
+    const int y = (blockIdx.y * GRX_ROWS + r) * 4 + (threadIdx.x >> 6);
+    if (!in || y >= H) continue;
+    const LinTap ty = lin_tap(y, scale_h, Hi);
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+      const float* r0 = pb + (c * sc + ty.i0 * sh);
+      const float* r1 = pb + (c * sc + ty.i1 * sh);
+      float v00[4], v01[4], v10[4], v11[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v00[j] = __ldg(r0 + tx[j].i0); v01[j] = __ldg(r0 + tx[j].i1);
+        v10[j] = __ldg(r1 + tx[j].i0); v11[j] = __ldg(r1 + tx[j].i1);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (div255) {
+          v00[j] = __fdiv_rn(v00[j], 255.f); v01[j] = __fdiv_rn(v01[j], 255.f);
+          v10[j] = __fdiv_rn(v10[j], 255.f); v11[j] = __fdiv_rn(v11[j], 255.f);
+        }
+        const float top = __fadd_rn(__fmul_rn(tx[j].l0, v00[j]), __fmul_rn(tx[j].l1, v01[j]));
+        const float bot = __fadd_rn(__fmul_rn(tx[j].l0, v10[j]), __fmul_rn(tx[j].l1, v11[j]));
+        g[j] = __fadd_rn(g[j], __fadd_rn(__fmul_rn(ty.l0, top), __fmul_rn(ty.l1, bot)));
+      }
+    }
+    if (C != 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) g[j] = __fdiv_rn(g[j], fc);
+    }
+    reinterpret_cast<float4*>(gray + ((int64_t)b * H + y) * (4 * (int64_t)W4))[x4] = make_float4(g[0], g[1], g[2], g[3]);
+    s += ((double)g[0] + (double)g[1]) + ((double)g[2] + (double)g[3]);
+    ss += ((double)g[0] * g[0] + (double)g[1] * g[1]) + ((double)g[2] * g[2] + (double)g[3] * g[3]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  __shared__ double sh_s[8], sh_ss[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh_s[warp] = s; sh_ss[warp] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += sh_s[i]; c2 += sh_ss[i]; }
+    atomicAdd(&stats[2 * b], a);
+    atomicAdd(&stats[2 * b + 1], c2);
+  }
+}
+
 // Fast path of gray_resize_kernel for the common case (BASELINE configs): fp32 input already at network resolution
 // (the bilinear resize is the identity: src == dst, lambda == 0), unit pixel stride, 16-byte aligned rows.
 // The image is walked as a linear array of 4-pixel groups (a 2-D block tiling left 7/8 of every second block idle at W = 640),
@@ -282,6 +353,11 @@ extern "C" int xfeat_preprocess_scaled(const void* d_img, int dtype, int B, int 
     dim3 g4(xf::cdiv(H * (W / 4), 256 * xf::GI_NPT), 1, B);
     xf::gray_identity_f32_kernel<<<g4, 256, 0, st>>>((const float*)d_img, C, stride_b, stride_c, stride_h, div255, H, W / 4,
                                                      d_xn, d_stats);
+  } else if (dtype == XF_DTYPE_F32 && stride_w == 1 &&
+             (int64_t)(C - 1) * stride_c + (int64_t)(Hi - 1) * stride_h + Wi < (int64_t)1 << 31 && stride_c >= 0 && stride_h >= 0) {
+    dim3 gx(xf::cdiv(W / 4, 64), xf::cdiv(H, 4 * xf::GRX_ROWS), B);
+    xf::gray_resize_f32x4_kernel<<<gx, 256, 0, st>>>((const float*)d_img, C, Hi, Wi, stride_b, (int)stride_c, (int)stride_h, div255,
+                                                     H, W / 4, sh, sw, d_xn, d_stats);
   } else if (dtype == XF_DTYPE_F32)
     xf::gray_resize_kernel<XF_DTYPE_F32><<<grid, 256, 0, st>>>(d_img, C, Hi, Wi, stride_b, stride_c, stride_h, stride_w,
                                                               div255, H, W, sh, sw, d_xn, d_stats);

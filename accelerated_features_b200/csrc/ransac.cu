@@ -18,6 +18,7 @@
 namespace xf {
 
 constexpr int RS_THREADS = 256, RS_WARPS = RS_THREADS / 32;
+constexpr int RS_E_REFITS = 8;         // local-optimisation rounds of the essential-matrix winner (ransac_e_final_kernel)
 constexpr int RS_MAX_PTS = 8192;       // correspondences per pair cached in shared memory (4 floats each)
 
 __device__ __forceinline__ uint32_t rs_hash(uint32_t x) {
@@ -485,13 +486,124 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_e_hyp_kernel(const float* _
   }
 }
 
+// Local optimisation of one essential-matrix candidate, by the whole block.  The 8-point fit of a minimal sample is noisy, so its
+// consensus set is only part of the true one: RS_E_REFITS rounds of a Sampson-weighted 8-point refit (rows scaled by 1/|grad|,
+// one IRLS step towards the Sampson error) over the points within mult*thr of the current model, mult shrinking 3 -> 1.  The model
+// kept is the one with the lowest MSAC cost at the true threshold, so the result is never worse than the candidate.
+// sE (shared, 9 floats): candidate in, optimised model out (visible to all threads on return).  Returns its MSAC cost.
+__device__ float rs_e_local_opt(const float4* __restrict__ sPts, int n, float t2, float* sE) {
+  __shared__ double sAcc[RS_WARPS][45];
+  __shared__ float sCost[RS_WARPS];
+  __shared__ float sBestE[9];
+  __shared__ int sCnt;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float best_cost = 3.0e38f;                         // block-uniform
+  __syncthreads();
+  for (int round = 0; round <= RS_E_REFITS; ++round) {
+    float E[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) E[k] = sE[k];
+    float cost = 0.f;                                // MSAC cost of the current model at the true threshold
+    for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+      const float4 c = sPts[i];
+      cost += fminf(rs_sampson2(E, c.x, c.y, c.z, c.w), t2);
+    }
+    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+    if (lane == 0) sCost[warp] = cost;
+    __syncthreads();
+    float total = 0.f;
+    for (int w = 0; w < RS_WARPS; ++w) total += sCost[w];      // same order in every thread
+    if (total < best_cost) {
+      best_cost = total;
+      if (threadIdx.x < 9) sBestE[threadIdx.x] = E[threadIdx.x];
+    }
+    if (round == RS_E_REFITS) break;
+    const float mult = round < 2 ? 3.0f : (round < 4 ? 2.0f : (round < 5 ? 1.5f : 1.0f));
+    const float t2r = t2 * mult * mult;
+    double acc[45];
+#pragma unroll
+    for (int k = 0; k < 45; ++k) acc[k] = 0.0;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+      const float4 c = sPts[i];
+      const float ea = E[0] * c.x + E[1] * c.y + E[2], eb = E[3] * c.x + E[4] * c.y + E[5];
+      const float ed = E[0] * c.z + E[3] * c.w + E[6], ef = E[1] * c.z + E[4] * c.w + E[7];
+      const float den = ea * ea + eb * eb + ed * ed + ef * ef;
+      if (rs_sampson2(E, c.x, c.y, c.z, c.w) < t2r && den > 1e-20f) {
+        ++cnt;
+        double r[9];
+        rs_epi_row(c.x, c.y, c.z, c.w, r);
+        const double wgt = 1.0 / (double)den;
+        int e = 0;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+          const double ra = r[a] * wgt;
+#pragma unroll
+          for (int b2 = a; b2 < 9; ++b2) acc[e++] += ra * r[b2];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 45; ++k) {
+      double v = acc[k];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sAcc[warp][k] = v;
+    }
+    if (threadIdx.x == 0) sCnt = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) atomicAdd(&sCnt, cnt);
+    __syncthreads();
+    if (sCnt < 8) break;                             // block-uniform
+    if (threadIdx.x == 0) {
+      double M[9][9], vec[9];
+      int e = 0;
+      for (int a = 0; a < 9; ++a)
+        for (int b2 = a; b2 < 9; ++b2) {
+          double v = 0.0;
+          for (int w = 0; w < RS_WARPS; ++w) v += sAcc[w][e];
+          M[a][b2] = v; M[b2][a] = v;
+          ++e;
+        }
+      rs_smallest_eigvec<9>(M, vec);
+      rs_project_essential(vec);
+      for (int k = 0; k < 9; ++k) sE[k] = (float)vec[k];
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) sE[threadIdx.x] = sBestE[threadIdx.x];
+  __syncthreads();
+  return best_cost;
+}
+
+// stage 2: every block's winner is optimised on its own (grid (blocks_per_pair, batch)) -- with w^8 all-inlier samples the raw
+// winners are few and noisy, and which of them converges to the full consensus set is not predictable from their raw cost.
+__global__ void __launch_bounds__(RS_THREADS) ransac_e_lo_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                                                 const int* __restrict__ np, int n_max, float thr,
+                                                                 RsRecord* __restrict__ best) {
+  extern __shared__ float4 sPts[];
+  __shared__ float sE[9];
+  const int pair = blockIdx.y;
+  const int n = min(np ? np[pair] : n_max, min(n_max, RS_MAX_PTS));
+  if (n < 8) return;
+  RsRecord* rec = best + (int64_t)pair * gridDim.x + blockIdx.x;
+  if (!(rec->cost < 3.0e38f)) return;                // this block found no hypothesis (block-uniform)
+  const float* q0 = p0 + (int64_t)pair * n_max * 2;
+  const float* q1 = p1 + (int64_t)pair * n_max * 2;
+  for (int i = threadIdx.x; i < n; i += RS_THREADS) sPts[i] = make_float4(q0[2 * i], q0[2 * i + 1], q1[2 * i], q1[2 * i + 1]);
+  if (threadIdx.x < 9) sE[threadIdx.x] = rec->m[threadIdx.x];
+  const float cost = rs_e_local_opt(sPts, n, thr * thr, sE);
+  if (threadIdx.x < 9) rec->m[threadIdx.x] = sE[threadIdx.x];
+  if (threadIdx.x == 0) rec->cost = cost;
+}
+
+// stage 3: the best optimised candidate classifies the correspondences.
 __global__ void __launch_bounds__(RS_THREADS) ransac_e_final_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
                                                                     const int* __restrict__ np, int n_max, float thr,
                                                                     const RsRecord* __restrict__ best, int blocks_per_pair,
                                                                     float* __restrict__ E_out, unsigned char* __restrict__ mask,
                                                                     int* __restrict__ n_inl) {
-  extern __shared__ float4 sPts[];
-  __shared__ double sAcc[RS_WARPS][45];
   __shared__ float sE[9];
   __shared__ int sCnt;
   const int pair = blockIdx.x;
@@ -508,7 +620,6 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_e_final_kernel(const float*
   }
   const float* q0 = p0 + (int64_t)pair * n_max * 2;
   const float* q1 = p1 + (int64_t)pair * n_max * 2;
-  for (int i = threadIdx.x; i < n; i += RS_THREADS) sPts[i] = make_float4(q0[2 * i], q0[2 * i + 1], q1[2 * i], q1[2 * i + 1]);
   if (threadIdx.x == 0) {
     RsRecord b = best[(int64_t)pair * blocks_per_pair];
     for (int k = 1; k < blocks_per_pair; ++k) {
@@ -516,72 +627,20 @@ __global__ void __launch_bounds__(RS_THREADS) ransac_e_final_kernel(const float*
       if (c.cost < b.cost) b = c;
     }
     for (int k = 0; k < 9; ++k) sE[k] = b.m[k];
+    sCnt = 0;
   }
   __syncthreads();
   const float t2 = thr * thr;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int round = 0; round < 2; ++round) {
-    float E[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) E[k] = sE[k];
-    double acc[45];
-#pragma unroll
-    for (int k = 0; k < 45; ++k) acc[k] = 0.0;
-    int cnt = 0;
-    for (int i = threadIdx.x; i < n; i += RS_THREADS) {
-      const float4 c = sPts[i];
-      if (rs_sampson2(E, c.x, c.y, c.z, c.w) < t2) {
-        ++cnt;
-        double r[9];
-        rs_epi_row(c.x, c.y, c.z, c.w, r);
-        int e = 0;
-#pragma unroll
-        for (int a = 0; a < 9; ++a)
-#pragma unroll
-          for (int b2 = a; b2 < 9; ++b2) acc[e++] += r[a] * r[b2];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 45; ++k) {
-      double v = acc[k];
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) sAcc[warp][k] = v;
-    }
-    const int total = __syncthreads_count(0) + 0;   // barrier
-    (void)total;
-    if (threadIdx.x == 0) sCnt = 0;
-    __syncthreads();
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) atomicAdd(&sCnt, cnt);
-    __syncthreads();
-    if (threadIdx.x == 0 && sCnt >= 8) {
-      double M[9][9], vec[9];
-      int e = 0;
-      for (int a = 0; a < 9; ++a)
-        for (int b2 = a; b2 < 9; ++b2) {
-          double v = 0.0;
-          for (int w = 0; w < RS_WARPS; ++w) v += sAcc[w][e];
-          M[a][b2] = v; M[b2][a] = v;
-          ++e;
-        }
-      rs_smallest_eigvec<9>(M, vec);
-      rs_project_essential(vec);
-      for (int k = 0; k < 9; ++k) sE[k] = (float)vec[k];
-    }
-    __syncthreads();
-  }
+  const int lane = threadIdx.x & 31;
   float E[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) E[k] = sE[k];
   int cnt = 0;
   for (int i = threadIdx.x; i < n; i += RS_THREADS) {
-    const float4 c = sPts[i];
-    const bool in = rs_sampson2(E, c.x, c.y, c.z, c.w) < t2;
+    const bool in = rs_sampson2(E, q0[2 * i], q0[2 * i + 1], q1[2 * i], q1[2 * i + 1]) < t2;
     mk[i] = in ? 1 : 0;
     cnt += in ? 1 : 0;
   }
-  if (threadIdx.x == 0) sCnt = 0;
-  __syncthreads();
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) atomicAdd(&sCnt, cnt);
   __syncthreads();
@@ -632,11 +691,13 @@ extern "C" int xfeat_ransac_essential(const float* d_x0, const float* d_x1, cons
   const int rounds = xf::cdiv(iters, bpp * xf::RS_WARPS * 32);
   const size_t smem = (size_t)n_max * sizeof(float4);
   XF_DYN_SMEM(xf::ransac_e_hyp_kernel, smem);
-  XF_DYN_SMEM(xf::ransac_e_final_kernel, smem);
+  XF_DYN_SMEM(xf::ransac_e_lo_kernel, smem);
   xf::ransac_e_hyp_kernel<<<dim3(bpp, batch), xf::RS_THREADS, smem, st>>>(d_x0, d_x1, d_n, n_max, thr, rounds, seed,
                                                                           (xf::RsRecord*)d_ws);
   XF_LAUNCH_CHECK();
-  xf::ransac_e_final_kernel<<<batch, xf::RS_THREADS, smem, st>>>(d_x0, d_x1, d_n, n_max, thr, (const xf::RsRecord*)d_ws, bpp, d_E,
+  xf::ransac_e_lo_kernel<<<dim3(bpp, batch), xf::RS_THREADS, smem, st>>>(d_x0, d_x1, d_n, n_max, thr, (xf::RsRecord*)d_ws);
+  XF_LAUNCH_CHECK();
+  xf::ransac_e_final_kernel<<<batch, xf::RS_THREADS, 0, st>>>(d_x0, d_x1, d_n, n_max, thr, (const xf::RsRecord*)d_ws, bpp, d_E,
                                                                  d_inliers, d_n_inliers);
   XF_LAUNCH_CHECK();
   return XF_OK;

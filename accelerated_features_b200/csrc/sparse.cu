@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(NM_WARPS * 32, 5) nms_march_kernel(const float
 constexpr int TS_THREADS = 1024, TS_BITS = 11, TS_BINS = 1 << TS_BITS;
 
 __global__ void __launch_bounds__(TS_THREADS) topk_select_sort_kernel(const unsigned long long* __restrict__ keys,
-                                                                      const int* __restrict__ n_keep, int cap, int top_k, int P,
-                                                                      unsigned long long* __restrict__ sorted) {
+                                                                      const int* __restrict__ n_keep, int n_const, int cap, int top_k,
+                                                                      int P, unsigned long long* __restrict__ sorted) {
   extern __shared__ unsigned long long sK[];   // [P], P = power of two >= top_k
   __shared__ int sHist[TS_BINS];
   __shared__ int sSel[2];                      // chosen digit, keys taken from the digits above it
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(TS_THREADS) topk_select_sort_kernel(const unsi
   using Scan = cub::BlockScan<int, TS_THREADS>;
   __shared__ typename Scan::TempStorage scan_tmp;
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int nk = n_keep[b];
+  const int nk = n_keep ? n_keep[b] : n_const;
   if (nk > cap) return;                        // candidate overflow: the sampler reports XF_N_OVERFLOW and reads nothing
   const int n = nk, k = min(n, top_k);
   const unsigned long long* kb = keys + (int64_t)b * cap;
@@ -387,6 +387,19 @@ __global__ void __launch_bounds__(TS_THREADS) topk_select_sort_kernel(const unsi
     }
   __syncthreads();
   for (int r = tid; r < k; r += TS_THREADS) sorted[(int64_t)b * cap + r] = sK[r];
+}
+
+// keys: B segments of `cap` slots, the first n_keep[b] (or n_const when n_keep is null) valid; sorted[b * cap + r], r < min(n, top_k)
+int launch_topk_select_sort(const unsigned long long* keys, const int* n_keep, int n_const, int cap, int top_k, int B,
+                            unsigned long long* sorted, cudaStream_t st) {
+  XF_REQUIRE(top_k > 0 && top_k <= 8192, "topk_select_sort: top_k %d out of range", top_k);
+  int P = 1;
+  while (P < top_k) P <<= 1;
+  const size_t smem_ts = (size_t)P * sizeof(unsigned long long);
+  XF_DYN_SMEM(topk_select_sort_kernel, smem_ts);
+  topk_select_sort_kernel<<<B, TS_THREADS, smem_ts, st>>>(keys, n_keep, n_const, cap, top_k, P, sorted);
+  XF_LAUNCH_CHECK();
+  return XF_OK;
 }
 
 __global__ void segment_offsets_kernel(const int* __restrict__ counts, int cap, int B, int* __restrict__ begin,
@@ -524,10 +537,10 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
 #pragma unroll
   for (int s = 8; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
   if (!live) return;
-  float4* dp = reinterpret_cast<float4*>(desc + slot * 64) + l16;
+  float4* dp = desc ? reinterpret_cast<float4*>(desc + slot * 64) + l16 : nullptr;   // desc == null: only the matcher's rows are wanted
   __half* sp = desc_split ? desc_split + ((int64_t)b * split_rows + r) * 128 + l16 * 4 : nullptr;
   if (!valid) {
-    *dp = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dp) *dp = make_float4(0.f, 0.f, 0.f, 0.f);
     if (sp) { *reinterpret_cast<uint2*>(sp) = make_uint2(0u, 0u); *reinterpret_cast<uint2*>(sp + 64) = make_uint2(0u, 0u); }
     if (l16 == 0) {
       kpts[slot * 2] = 0.f; kpts[slot * 2 + 1] = 0.f; scores[slot] = 0.f;
@@ -537,7 +550,7 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
   }
   const float dn = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));  // F.normalize(feats, dim=-1), xfeat.py:93
   const float4 dv = make_float4(o.x * dn, o.y * dn, o.z * dn, o.w * dn);
-  *dp = dv;
+  if (dp) *dp = dv;
   if (sp) store_desc_split(sp, dv);
   if (l16 == 0) {
     kpts[slot * 2] = __fmul_rn((float)x, rw);  // mkpts * [rw, rh], xfeat.py:96
@@ -614,7 +627,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
       const int64_t slot = (int64_t)b * top_k + r;
       const float dn = __fdiv_rn(1.0f, fmaxf(sqrtf(ss), 1e-12f));  // F.normalize(feats, dim=-1), xfeat.py:93
       const float4 dv = make_float4(o.x * dn, o.y * dn, o.z * dn, o.w * dn);
-      reinterpret_cast<float4*>(desc + slot * 64)[l16] = dv;
+      if (desc) reinterpret_cast<float4*>(desc + slot * 64)[l16] = dv;
       if (desc_split) store_desc_split(desc_split + ((int64_t)b * split_rows + r) * 128 + l16 * 4, dv);
       if (l16 == 0) {
         kpts[slot * 2] = __fmul_rn((float)x, rw);  // mkpts * [rw, rh], xfeat.py:96
@@ -631,7 +644,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
   // zero-fill the slots past n_valid
   for (int64_t e = (int64_t)nv * 16 + tid; e < (int64_t)top_k * 16; e += SAMPLE_THREADS) {
     const int64_t slot = (int64_t)b * top_k + (e >> 4);
-    reinterpret_cast<float4*>(desc + slot * 64)[e & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (desc) reinterpret_cast<float4*>(desc + slot * 64)[e & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
     if ((e & 15) == 0) {
       kpts[slot * 2] = 0.f; kpts[slot * 2 + 1] = 0.f; scores[slot] = 0.f;
       if (kpts_int) { kpts_int[slot * 2] = 0; kpts_int[slot * 2 + 1] = 0; }
@@ -696,7 +709,7 @@ extern "C" int xfeat_detect_sparse_split(xfeat_ctx* ctx, const float* d_feats, c
                                          void* stream) {
   XF_REQUIRE(d_desc_split == nullptr || (split_rows >= top_k && split_rows % 512 == 0),
              "detect_sparse: split_rows must be a multiple of 512 and >= top_k (got %d)", split_rows);
-  XF_REQUIRE(ctx && d_feats && d_heat && d_reliability && d_kpts && d_scores && d_desc && d_n_valid && d_ws,
+  XF_REQUIRE(ctx && d_feats && d_heat && d_reliability && d_kpts && d_scores && (d_desc || d_desc_split) && d_n_valid && d_ws,
              "detect_sparse: null pointer");
   XF_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0 && top_k > 0,
              "detect_sparse: bad shape B=%d H=%d W=%d top_k=%d", B, H, W, top_k);
@@ -727,12 +740,7 @@ extern "C" int xfeat_detect_sparse_split(xfeat_ctx* ctx, const float* d_feats, c
   XF_LAUNCH_CHECK();
   static const bool force_cub = getenv("XFEAT_TOPK_CUB") != nullptr;   // A/B switch: the capacity-wide segmented sort
   if (!force_cub && top_k <= 8192) {
-    int P = 1;
-    while (P < top_k) P <<= 1;
-    const size_t smem_ts = (size_t)P * sizeof(unsigned long long);
-    XF_DYN_SMEM(xf::topk_select_sort_kernel, smem_ts);
-    xf::topk_select_sort_kernel<<<B, xf::TS_THREADS, smem_ts, st>>>(ws.keys, ws.n_keep, cap, top_k, P, ws.sorted);
-    XF_LAUNCH_CHECK();
+    if ((rc = xf::launch_topk_select_sort(ws.keys, ws.n_keep, 0, cap, top_k, B, ws.sorted, st))) return rc;
   } else {
     xf::segment_offsets_kernel<<<xf::cdiv(B, 128), 128, 0, st>>>(ws.n_keep, cap, B, ws.seg_begin, ws.seg_end);
     XF_LAUNCH_CHECK();

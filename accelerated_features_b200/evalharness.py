@@ -102,9 +102,10 @@ def estimate_pose_opencv(kpts0, kpts1, K0, K1, thresh, conf=0.99999):
     return ret
 
 
-def estimate_pose_gpu(kpts0, kpts1, K0, K1, thresh, iters: int = 2048, seed: int = 0):
+def estimate_pose_gpu(kpts0, kpts1, K0, K1, thresh, iters: int = 8192, seed: int = 0):
     """estimate_pose_poselib's role (megadepth1500.py:98-113) on the GPU: essential-matrix RANSAC (geometry.find_essential_batch,
-    8-point + Sampson + re-fit) and the cheirality test.  Same signature / return as estimate_pose_opencv."""
+    8-point + Sampson + re-fit) and the cheirality test.  Same signature / return as estimate_pose_opencv.  An 8-point sample is
+    all-inlier with probability w^8 (0.4 % at w = 0.5, against 3 % for a 5-point solver): hence the default of 8192 hypotheses."""
     import torch
     from .geometry import find_essential_batch, recover_pose
     if len(kpts0) < 8:

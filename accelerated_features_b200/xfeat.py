@@ -21,6 +21,7 @@ from . import _lib
 from . import weights as _weights
 
 _F32 = np.float32
+_D2H_ON_MAIN = bool(__import__("os").environ.get("XFEAT_STREAM_D2H_MAIN"))   # A/B switch of match_xfeat_stream (results on the compute stream)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -231,7 +232,8 @@ class XFeat(torch.nn.Module):
     def _split_rows(top_k: int) -> int:
         return (top_k + 511) // 512 * 512                       # row padding of the tensor-core matcher (mnn_tc.cu)
 
-    def _detect_sparse_device(self, x, top_k: int, detection_threshold: float, div255=False, want_split: bool = False):
+    def _detect_sparse_device(self, x, top_k: int, detection_threshold: float, div255=False, want_split: bool = False,
+                              want_desc: bool = True):
         """Whole sparse extraction on the device, fixed-capacity outputs, no host sync.  `x` is one image batch or a list
         of batches of identical shape (they are normalised into one activation batch without concatenating the inputs);
         `div255` is one flag or one per batch (parse_input's "/255" applies to numpy inputs only, xfeat.py:400-401).
@@ -259,7 +261,7 @@ class XFeat(torch.nn.Module):
         feats, heat, rel, _ = self._run_net(xn, B, H, W)
         kpts = self._empty((B, top_k, 2))
         scores = self._empty((B, top_k))
-        desc = self._empty((B, top_k, 64))
+        desc = self._empty((B, top_k, 64)) if (want_desc or not want_split) else None   # match-only callers take the split rows alone
         n_valid = self._empty((B,), torch.int32)
         n_cand = self._empty((B,), torch.int32)
         nbytes = self._lib.xfeat_sparse_workspace_bytes(B, H, W, top_k)
@@ -271,7 +273,7 @@ class XFeat(torch.nn.Module):
         with torch.cuda.device(self.dev):
             _lib.check(self._lib.xfeat_detect_sparse_split(self._ctx, feats.data_ptr(), heat.data_ptr(), rel.data_ptr(), B, H, W,
                                                            top_k, float(detection_threshold), float(_F32(rw)), float(_F32(rh)),
-                                                           kpts.data_ptr(), scores.data_ptr(), desc.data_ptr(),
+                                                           kpts.data_ptr(), scores.data_ptr(), _ptr(desc),
                                                            n_valid.data_ptr(), n_cand.data_ptr(), None, _ptr(split),
                                                            split_rows if want_split else 0, ws.data_ptr(),
                                                            ws.numel(), self._stream()), "xfeat_detect_sparse_split")
@@ -354,10 +356,12 @@ class XFeat(torch.nn.Module):
             raise RuntimeError("the two image sets must have the same batch size")
         if x1.shape[1:] == x2.shape[1:]:
             presplit = self._lib.xfeat_get_mnn_impl() in (1, 3)     # the sampler writes the matcher's operand rows itself
-            o = self._detect_sparse_device([x1, x2], top_k, self.detection_threshold, [da, db], want_split=presplit)
+            o = self._detect_sparse_device([x1, x2], top_k, self.detection_threshold, [da, db], want_split=presplit,
+                                           want_desc=not presplit)
             k1, k2 = o["keypoints"][:B], o["keypoints"][B:]
-            d1, d2 = o["descriptors"][:B], o["descriptors"][B:]
             n1, n2 = o["n_valid"][:B], o["n_valid"][B:]
+            if not presplit:
+                d1, d2 = o["descriptors"][:B], o["descriptors"][B:]
             if presplit:
                 sp = o["desc_split"]
                 idx0, idx1, cnt = self._mnn_presplit_device(sp[:B], n1, sp[B:], n2, top_k, sp.shape[1], B, min_cossim)
@@ -440,6 +444,9 @@ class XFeat(torch.nn.Module):
             self.ready = [torch.cuda.Event(), torch.cuda.Event()]
             self.freed = [torch.cuda.Event(), torch.cuda.Event()]
             self.res = [None, None]              # pinned (mk0, mk1, cnt)
+            self.res_dev = [None, None]          # the device tensors being copied out (kept alive until the copy has finished)
+            self.d2h = torch.cuda.Stream(dev)    # results leave on their own stream: the next batch's kernels do not queue behind them
+            self.computed = [torch.cuda.Event(), torch.cuda.Event()]
             self.done = [torch.cuda.Event(), torch.cuda.Event()]
 
     def pinned_like(self, shape, dtype=torch.uint8) -> torch.Tensor:
@@ -520,10 +527,12 @@ class XFeat(torch.nn.Module):
 
         def finish(slot):
             pipe.done[slot].synchronize()
+            pipe.res_dev[slot] = None
             r0, r1, rc = pipe.res[slot]
             c = rc.tolist()
             self._check_counts(c, "match_xfeat_stream")
-            return [(r0[b, :c[b]].numpy().copy(), r1[b, :c[b]].numpy().copy()) for b in range(len(c))]
+            a0, a1 = r0.numpy(), r1.numpy()              # one view per buffer, one copy per pair and side
+            return [(a0[b, :c[b]].copy(), a1[b, :c[b]].copy()) for b in range(len(c))]
 
         try:
             nxt = next(it)
@@ -549,10 +558,15 @@ class XFeat(torch.nn.Module):
                        torch.empty(mk1.shape, dtype=torch.float32, pin_memory=True),
                        torch.empty((B,), dtype=torch.int32, pin_memory=True))
                 pipe.res[slot] = res
-            res[0].copy_(mk0, non_blocking=True)
-            res[1].copy_(mk1, non_blocking=True)
-            res[2].copy_(cnt, non_blocking=True)
-            pipe.done[slot].record(main)
+            pipe.computed[slot].record(main)
+            pipe.res_dev[slot] = (mk0, mk1, cnt)
+            out_stream = main if _D2H_ON_MAIN else pipe.d2h
+            with torch.cuda.stream(out_stream):
+                out_stream.wait_event(pipe.computed[slot])
+                res[0].copy_(mk0, non_blocking=True)
+                res[1].copy_(mk1, non_blocking=True)
+                res[2].copy_(cnt, non_blocking=True)
+                pipe.done[slot].record(out_stream)
             if pending is not None:
                 yield finish(pending)
             pending = slot

@@ -248,20 +248,23 @@ def run_gpu(args):
             idx0, idx1, cnt = xf._mnn_device(o1["descriptors"], None, K, K * 64, o2["descriptors"], None, K, K * 64, BATCH, -1)
             m, n_ref = xf._refine_device(o1, o2, idx0, idx1, cnt)
             return m, n_ref, cnt
-        o = xf._detect_sparse_device([d1, d2], TOPK, xf.detection_threshold)
+        presplit = lib.xfeat_get_mnn_impl() in (1, 3)       # the same kernel sequence as XFeat._match_sparse_batch_device
+        o = xf._detect_sparse_device([d1, d2], TOPK, xf.detection_threshold, want_split=presplit, want_desc=not presplit)
         k1, k2 = o["keypoints"][:BATCH], o["keypoints"][BATCH:]
-        f1, f2 = o["descriptors"][:BATCH], o["descriptors"][BATCH:]
         n1, n2 = o["n_valid"][:BATCH], o["n_valid"][BATCH:]
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        idx0, idx1, cnt = xf._mnn_device(f1, n1, TOPK, TOPK * 64, f2, n2, TOPK, TOPK * 64, BATCH, -1, abs_bound=1.0)
+        if presplit:
+            sp = o["desc_split"]
+            idx0, idx1, cnt = xf._mnn_presplit_device(sp[:BATCH], n1, sp[BATCH:], n2, TOPK, sp.shape[1], BATCH, -1)
+        else:
+            f1, f2 = o["descriptors"][:BATCH], o["descriptors"][BATCH:]
+            idx0, idx1, cnt = xf._mnn_device(f1, n1, TOPK, TOPK * 64, f2, n2, TOPK, TOPK * 64, BATCH, -1, abs_bound=1.0)
         if record:
             e1.record()
             dom_events.append((e0, e1))
-        mk0, mk1 = xf._empty((BATCH, TOPK, 2)), xf._empty((BATCH, TOPK, 2))
-        _lib.check(lib.xfeat_gather_matches(k1.data_ptr(), k2.data_ptr(), TOPK, TOPK, idx0.data_ptr(), idx1.data_ptr(),
-                                            cnt.data_ptr(), BATCH, mk0.data_ptr(), mk1.data_ptr(), xf._stream()), "gather")
+        mk0, mk1, cnt = xf._gather_matches(k1, k2, idx0, idx1, cnt, BATCH, TOPK)
         return mk0, mk1, cnt, n1, n2
 
     warm = max(args.warmup, 3)
@@ -360,7 +363,8 @@ def run_gpu(args):
         else:
             flops = 2.0 * 64.0 * float((out[3].double() * out[4].double()).sum())
             impl = lib.xfeat_get_mnn_impl()
-            kname = f"xfeat_mnn_match (impl {impl}): fused D1.D2^T + row/col arg-max on tcgen05; timed call also contains split/finalize"
+            kname = (f"xfeat_mnn_match_presplit (impl {impl}): mnn_tc_persist_kernel, fused D1.D2^T (3-term split fp16) + row arg-max, both "
+                     "directions, tcgen05; timed call also contains the finalize kernel")
             cfg_extra = {"mean_keypoints": [float(out[3].float().mean()), float(out[4].float().mean())],
                          "mean_matches_per_pair": float(out[2].float().mean())}
             d2h = int(2 * BATCH * TOPK * 2 * 4 + BATCH * 4)

@@ -203,7 +203,7 @@ def test_ransac_essential_pose_vs_opencv():
     worst = 0.0
     for n, frac in [(2000, 0.6), (1200, 0.45), (600, 0.7), (300, 0.5)]:
         p0, p1, inl, K, T = synth_two_view(rng, n, frac, 0.5)
-        got = estimate_pose_gpu(p0, p1, K, K, 1.5, iters=2048, seed=5)
+        got = estimate_pose_gpu(p0, p1, K, K, 1.5, iters=16384, seed=5)   # 8-point samples: 0.45^8 = 0.17 % all-inlier
         cv2.setRNGSeed(1)
         ref = estimate_pose_opencv(p0, p1, K, K, 1.5)
         assert got is not None and ref is not None
