@@ -1,5 +1,9 @@
+"""GPU essential-matrix RANSAC against the ground-truth model on the synthetic two-view scenes of tests/test_gpu_geometry.py: MSAC cost
+and inlier recall of xfeat_ransac_essential next to the true E, then a numpy replay of the local optimisation from the returned model.
+    python tools/essential_check.py      (one GPU)"""
 import numpy as np, cv2, sys, torch
-sys.path.insert(0,'/root/repo')
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 from tests.test_gpu_geometry import synth_two_view
 from accelerated_features_b200.geometry import find_essential_batch
 def proj_E(E):
