@@ -302,11 +302,15 @@ def run_gpu(args):
                 tot += sum(int(r.shape[0]) for r in res)                  # (the counts are the D2H read of the result)
             return tot
         tot = 0
+        stamps = [time.perf_counter()]
         for res in xf.match_xfeat_stream(((a, b) for _ in range(n)), top_k=TOPK):
             tot += len(res)
+            stamps.append(time.perf_counter())
+        if os.environ.get("XFEAT_BENCH_DEBUG"):
+            print("e2e batch intervals (ms):", [round(1e3 * (y - x), 2) for x, y in zip(stamps, stamps[1:])], file=sys.stderr)
         return tot
 
-    e2e_public(2, h1, h2)
+    e2e_public(max(3, args.warmup), h1, h2)
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
@@ -321,7 +325,7 @@ def run_gpu(args):
         hu1.copy_((torch.rand(BATCH, H, W, 3, generator=g) * 255).to(torch.uint8))
         hu2.copy_((torch.rand(BATCH, H, W, 3, generator=g) * 255).to(torch.uint8))
         n1u, n2u = hu1.numpy(), hu2.numpy()                                # numpy views of pinned memory
-        e2e_public(2, n1u, n2u)
+        e2e_public(max(3, args.warmup), n1u, n2u)
         barrier()
         v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         v0.record()
