@@ -119,6 +119,23 @@ __device__ __forceinline__ float sparse_src_coord(int p, int size_pos, int size_
 }
 
 // ATen upsample_bilinear2d source index (align_corners=False): src = scale*(dst+0.5)-0.5 clamped at 0.
+// packed fp32 pairs (sm_100: FFMA2 / FMUL2): two independent IEEE round-to-nearest operations per instruction
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return r;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  float2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&r))
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return r;
+}
+
 struct LinTap {
   int i0, i1;
   float l0, l1;

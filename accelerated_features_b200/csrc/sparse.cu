@@ -455,21 +455,24 @@ __device__ __forceinline__ float4 bicubic4(const float* __restrict__ fb, const f
     // the same arithmetic in the same order as the general path below (the kernel is issue-bound: ncu 75 % issue-active)
     const float4* p0 = reinterpret_cast<const float4*>(fb) + (uint32_t)(y0 * Wm + x0) * 16u + (uint32_t)l16;
     const float* d0 = db + (uint32_t)(y0 * Wm + x0);
+    // packed fp32 pairs (FMUL2 / FFMA2): per component the same IEEE operations in the same order as the scalar form below
+    float2 oa = make_float2(0.f, 0.f), ob = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+      float2 ra = make_float2(0.f, 0.f), rb = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float4 v = __ldg(p0 + (uint32_t)(i * Wm + j) * 16u);
+        const float4 v = __ldg(p0 + (uint32_t)(i * Wm + j) * 16u);
         const float d = __ldg(d0 + (uint32_t)(i * Wm + j));
-        v.x *= d; v.y *= d; v.z *= d; v.w *= d;
-        rr.x = fmaf(v.x, cx[j], rr.x); rr.y = fmaf(v.y, cx[j], rr.y);
-        rr.z = fmaf(v.z, cx[j], rr.z); rr.w = fmaf(v.w, cx[j], rr.w);
+        const float2 dd = make_float2(d, d), cc = make_float2(cx[j], cx[j]);
+        ra = f2_fma(f2_mul(make_float2(v.x, v.y), dd), cc, ra);
+        rb = f2_fma(f2_mul(make_float2(v.z, v.w), dd), cc, rb);
       }
-      o.x = fmaf(rr.x, cy[i], o.x); o.y = fmaf(rr.y, cy[i], o.y);
-      o.z = fmaf(rr.z, cy[i], o.z); o.w = fmaf(rr.w, cy[i], o.w);
+      const float2 cyy = make_float2(cy[i], cy[i]);
+      oa = f2_fma(ra, cyy, oa);
+      ob = f2_fma(rb, cyy, ob);
     }
-    return o;
+    return make_float4(oa.x, oa.y, ob.x, ob.y);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -565,8 +568,11 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
 // L1 instead of L2 (5x5 NMS puts keypoints >= 3 px apart while a feature cell covers 8 px).  Results go to the slot given
 // by the score rank, exactly as in the generic kernel.
 // (Sharing an image between 4 CTAs of 512 threads, each repeating the bucketing, measured 321 us vs 268 us: not kept.)
-constexpr int SAMPLE_MAX_K = 8192, SAMPLE_THREADS = 1024, SAMPLE_MAX_ROWS = 512;
-__global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
+// 256-thread CTAs, SAMPLE_PARTS per image (each rebuilds the image's spatial order -- 4096 shared-memory atomics -- and samples its
+// share of it): 4 CTAs per SM by registers, and the 128 x 8 CTAs of the BASELINE batch spread over all 148 SMs, where one
+// 1024-thread CTA per image left 20 SMs idle.
+constexpr int SAMPLE_MAX_K = 8192, SAMPLE_THREADS = 256, SAMPLE_MAX_ROWS = 512, SAMPLE_PARTS = 8;
+__global__ void __launch_bounds__(SAMPLE_THREADS, 4) sample_desc_sorted_kernel(
     const unsigned long long* __restrict__ sorted, const int* __restrict__ n_keep, const float* __restrict__ feats,
     const float* __restrict__ den, int H, int W, int Hm, int Wm, int cap, int top_k, float rw, float rh, float* __restrict__ kpts,
     float* __restrict__ scores, float* __restrict__ desc, int* __restrict__ n_valid, int* __restrict__ kpts_int,
@@ -575,10 +581,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
   unsigned long long* sKey = reinterpret_cast<unsigned long long*>(sm_raw);           // [top_k]
   unsigned short* sOrder = reinterpret_cast<unsigned short*>(sKey + top_k);            // [top_k]
   __shared__ int sHist[SAMPLE_MAX_ROWS];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, part = blockIdx.y, nparts = gridDim.y;
   const int nk = n_keep[b];
   const int nv = nk > cap ? 0 : min(nk, top_k);   // candidate overflow: nothing is trusted, n_valid = XF_N_OVERFLOW (header)
-  if (tid == 0) n_valid[b] = nk > cap ? -1 : nv;
+  if (tid == 0 && part == 0) n_valid[b] = nk > cap ? -1 : nv;
   for (int i = tid; i < SAMPLE_MAX_ROWS; i += SAMPLE_THREADS) sHist[i] = 0;
   __syncthreads();
   for (int r = tid; r < nv; r += SAMPLE_THREADS) {
@@ -609,11 +615,35 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
     sOrder[pos] = (unsigned short)r;
   }
   __syncthreads();
+  // This CTA's share of the spatially ordered list.  The order INSIDE a row bucket depends on the atomics' arrival order and
+  // differs between the CTAs of an image, so shares are cut at bucket ends (sHist[i] now holds the end offset of bucket i, a
+  // function of the counts alone): share p = [first end >= p*nv/parts, first end >= (p+1)*nv/parts).
+  __shared__ int sRange[2];
+  if (tid < 32) {
+    const int tl = (int)((int64_t)part * nv / nparts), th = (int)((int64_t)(part + 1) * nv / nparts);
+    int ml = nv, mh = nv;
+    for (int i = tid; i < SAMPLE_MAX_ROWS; i += 32) {
+      const int e = sHist[i];
+      if (e >= tl) ml = min(ml, e);
+      if (e >= th) mh = min(mh, e);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ml = min(ml, __shfl_xor_sync(0xffffffffu, ml, o));
+      mh = min(mh, __shfl_xor_sync(0xffffffffu, mh, o));
+    }
+    if (tid == 0) {
+      sRange[0] = part == 0 ? 0 : ml;
+      sRange[1] = part == nparts - 1 ? nv : mh;
+    }
+  }
+  __syncthreads();
+  const int lo = sRange[0], hi = sRange[1];
   const int l16 = tid & 15, grp = tid >> 4, ngrp = SAMPLE_THREADS / 16;
   const float* fb = feats + (int64_t)b * Hm * Wm * 64;
   const float* db = den + (int64_t)b * Hm * Wm;
-  for (int i = grp; i < ((nv + 1) & ~1); i += ngrp) {   // both half-warps of a warp iterate together (shuffles below)
-    const bool valid = i < nv;
+  for (int i = lo + grp; i < lo + ((hi - lo + 1) & ~1); i += ngrp) {   // both half-warps of a warp iterate together (shuffles below)
+    const bool valid = i < hi;
     const int r = valid ? (int)sOrder[i] : 0;
     const unsigned long long key = sKey[valid ? r : 0];
     const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
@@ -639,10 +669,11 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_desc_sorted_kernel(
   }
   if (desc_split) {   // rows past n_valid up to the matcher's row padding are zero operands
     uint4* zp = reinterpret_cast<uint4*>(desc_split + ((int64_t)b * split_rows + nv) * 128);
-    for (int64_t e = tid; e < (int64_t)(split_rows - nv) * 16; e += SAMPLE_THREADS) zp[e] = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t e = tid + (int64_t)part * SAMPLE_THREADS; e < (int64_t)(split_rows - nv) * 16; e += (int64_t)SAMPLE_THREADS * nparts)
+      zp[e] = make_uint4(0u, 0u, 0u, 0u);
   }
   // zero-fill the slots past n_valid
-  for (int64_t e = (int64_t)nv * 16 + tid; e < (int64_t)top_k * 16; e += SAMPLE_THREADS) {
+  for (int64_t e = (int64_t)nv * 16 + tid + (int64_t)part * SAMPLE_THREADS; e < (int64_t)top_k * 16; e += (int64_t)SAMPLE_THREADS * nparts) {
     const int64_t slot = (int64_t)b * top_k + (e >> 4);
     if (desc) reinterpret_cast<float4*>(desc + slot * 64)[e & 15] = make_float4(0.f, 0.f, 0.f, 0.f);
     if ((e & 15) == 0) {
@@ -757,7 +788,8 @@ extern "C" int xfeat_detect_sparse_split(xfeat_ctx* ctx, const float* d_feats, c
   if (!force_generic && B >= 32 && top_k <= xf::SAMPLE_MAX_K && Hm <= xf::SAMPLE_MAX_ROWS) {
     const size_t smem = (size_t)top_k * (sizeof(unsigned long long) + sizeof(unsigned short));
     XF_DYN_SMEM(xf::sample_desc_sorted_kernel, smem);
-    xf::sample_desc_sorted_kernel<<<B, xf::SAMPLE_THREADS, smem, st>>>(ws.sorted, ws.n_keep, d_feats, ws.den, H, W, Hm, Wm, cap,
+    const int parts = std::max(1, std::min(xf::SAMPLE_PARTS, top_k / 512));
+    xf::sample_desc_sorted_kernel<<<dim3(B, parts), xf::SAMPLE_THREADS, smem, st>>>(ws.sorted, ws.n_keep, d_feats, ws.den, H, W, Hm, Wm, cap,
                                                                       top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid,
                                                                       d_kpts_int, (__half*)d_desc_split, split_rows);
   } else {

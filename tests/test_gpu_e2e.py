@@ -165,6 +165,11 @@ def test_full_size_properties(xf):
     x2 = torch.randn(64, 3, 480, 640, generator=g)
     o = xf._detect_sparse_device(torch.cat([x1[:8], x2[:8]]), 4096, 0.05)
     d = o["descriptors"]; n = o["n_valid"].tolist()
+    # B >= 32 runs the multi-CTA-per-image spatially ordered sampler, B = 8 the generic one: same arithmetic, same bits
+    o32 = xf._detect_sparse_device(torch.cat([x1[:16], x2[:16]]), 4096, 0.05)
+    o8 = xf._detect_sparse_device(x2[:8], 4096, 0.05)
+    for k in ("keypoints", "scores", "descriptors", "n_valid"):
+        assert torch.equal(o32[k][16:24], o8[k]), k
     nrm = d[0, :n[0]].norm(dim=-1)
     assert float((nrm - 1).abs().max()) < 1e-5                         # unit descriptors
     s = o["scores"][0, :n[0]]
