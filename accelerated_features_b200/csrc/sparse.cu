@@ -441,6 +441,9 @@ __global__ void __launch_bounds__(256) feat_norm_kernel(const float* __restrict_
 
 // Bicubic sample (ATen grid_sampler_2d, A = -0.75, zeros padding) of the channel-normalised map at pixel (x, y), for the 4
 // channels owned by lane l16 of a 16-lane group; returns the un-normalised 4-vector and the group-wide sum of squares.
+// UNIFORM: every lane of the warp calls (with valid coordinates), so the interior test can be made warp-wide and the two
+// half-warps of a keypoint pair never run both paths one after the other.
+template <bool UNIFORM>
 __device__ __forceinline__ float4 bicubic4(const float* __restrict__ fb, const float* __restrict__ db, int x, int y, int H, int W,
                                            int Hm, int Wm, int l16) {
   const float ix = sparse_src_coord(x, W, Wm), iy = sparse_src_coord(y, H, Hm);
@@ -449,14 +452,15 @@ __device__ __forceinline__ float4 bicubic4(const float* __restrict__ fb, const f
   const int x0 = (int)fx - 1, y0 = (int)fy - 1;
   const float cx[4] = {cubic2(tx + 1.f), cubic1(tx), cubic1(1.f - tx), cubic2((1.f - tx) + 1.f)};
   const float cy[4] = {cubic2(ty + 1.f), cubic1(ty), cubic1(1.f - ty), cubic2((1.f - ty) + 1.f)};
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (x0 >= 0 && x0 + 3 < Wm && y0 >= 0 && y0 + 3 < Hm) {
-    // interior keypoint (almost all): no per-tap bounds tests, 32-bit offsets from one base pointer -- the same loads and
-    // the same arithmetic in the same order as the general path below (the kernel is issue-bound: ncu 75 % issue-active)
-    const float4* p0 = reinterpret_cast<const float4*>(fb) + (uint32_t)(y0 * Wm + x0) * 16u + (uint32_t)l16;
+  bool interior = x0 >= 0 && x0 + 3 < Wm && y0 >= 0 && y0 + 3 < Hm;
+  if (UNIFORM) interior = __all_sync(0xffffffffu, interior);
+  const float4* f4 = reinterpret_cast<const float4*>(fb) + (uint32_t)l16;
+  // packed fp32 pairs (FMUL2 / FFMA2): per component  v*d, then fma(v*d, cx[j], row), then fma(row, cy[i], out)
+  float2 oa = make_float2(0.f, 0.f), ob = make_float2(0.f, 0.f);
+  if (interior) {
+    // interior keypoint (almost all): no per-tap tests, 32-bit offsets from one base pointer
+    const float4* p0 = f4 + (uint32_t)(y0 * Wm + x0) * 16u;
     const float* d0 = db + (uint32_t)(y0 * Wm + x0);
-    // packed fp32 pairs (FMUL2 / FFMA2): per component the same IEEE operations in the same order as the scalar form below
-    float2 oa = make_float2(0.f, 0.f), ob = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float2 ra = make_float2(0.f, 0.f), rb = make_float2(0.f, 0.f);
@@ -474,26 +478,37 @@ __device__ __forceinline__ float4 bicubic4(const float* __restrict__ fb, const f
     }
     return make_float4(oa.x, oa.y, ob.x, ob.y);
   }
+  // border keypoint: taps outside the map add nothing (grid_sample zeros padding).  The address is clamped into the map and the
+  // tap's normaliser d is replaced by 0, so the same instruction sequence runs (v*0 = +-0, and row + (+-0 * c) == row bit for
+  // bit: the accumulators start at +0) -- 16 unconditional taps instead of 16 predicated ones with 64-bit addressing.
+  uint32_t xo[4], yo[4];
+  bool vx[4], vy[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int xx = x0 + k, yy = y0 + k;
+    vx[k] = xx >= 0 && xx < Wm;
+    vy[k] = yy >= 0 && yy < Hm;
+    xo[k] = (uint32_t)min(max(xx, 0), Wm - 1);
+    yo[k] = (uint32_t)min(max(yy, 0), Hm - 1) * (uint32_t)Wm;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int yy = y0 + i;
-    float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 ra = make_float2(0.f, 0.f), rb = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int xx = x0 + j;
-      if (yy >= 0 && yy < Hm && xx >= 0 && xx < Wm) {  // zeros padding
-        const int64_t p = (int64_t)yy * Wm + xx;
-        float4 v = __ldg(reinterpret_cast<const float4*>(fb + p * 64) + l16);
-        const float d = __ldg(db + p);                 // 1 / F.normalize(M1, dim=1) denominator, xfeat.py:70
-        v.x *= d; v.y *= d; v.z *= d; v.w *= d;
-        rr.x = fmaf(v.x, cx[j], rr.x); rr.y = fmaf(v.y, cx[j], rr.y);
-        rr.z = fmaf(v.z, cx[j], rr.z); rr.w = fmaf(v.w, cx[j], rr.w);
-      }
+      const uint32_t off = yo[i] + xo[j];
+      const float4 v = __ldg(f4 + off * 16u);
+      float d = __ldg(db + off);                 // 1 / F.normalize(M1, dim=1) denominator, xfeat.py:70
+      if (!(vx[j] && vy[i])) d = 0.f;
+      const float2 dd = make_float2(d, d), cc = make_float2(cx[j], cx[j]);
+      ra = f2_fma(f2_mul(make_float2(v.x, v.y), dd), cc, ra);
+      rb = f2_fma(f2_mul(make_float2(v.z, v.w), dd), cc, rb);
     }
-    o.x = fmaf(rr.x, cy[i], o.x); o.y = fmaf(rr.y, cy[i], o.y);
-    o.z = fmaf(rr.z, cy[i], o.z); o.w = fmaf(rr.w, cy[i], o.w);
+    const float2 cyy = make_float2(cy[i], cy[i]);
+    oa = f2_fma(ra, cyy, oa);
+    ob = f2_fma(rb, cyy, ob);
   }
-  return o;
+  return make_float4(oa.x, oa.y, ob.x, ob.y);
 }
 
 // Half a warp per output slot (b, r): lane owns 4 channels. feats: (B,Hm,Wm,64) NHWC un-normalised, den: (B,Hm,Wm).
@@ -534,7 +549,7 @@ __global__ void __launch_bounds__(256) sample_desc_kernel(const unsigned long lo
     key = sorted[(int64_t)b * cap + r];
     const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
     x = (int)(lin % (uint32_t)W); y = (int)(lin / (uint32_t)W);
-    o = bicubic4(feats + (int64_t)b * Hm * Wm * 64, den + (int64_t)b * Hm * Wm, x, y, H, W, Hm, Wm, l16);
+    o = bicubic4<false>(feats + (int64_t)b * Hm * Wm * 64, den + (int64_t)b * Hm * Wm, x, y, H, W, Hm, Wm, l16);
   }
   float ss = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
 #pragma unroll
@@ -585,13 +600,21 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 4) sample_desc_sorted_kernel(
   const int nk = n_keep[b];
   const int nv = nk > cap ? 0 : min(nk, top_k);   // candidate overflow: nothing is trusted, n_valid = XF_N_OVERFLOW (header)
   if (tid == 0 && part == 0) n_valid[b] = nk > cap ? -1 : nv;
+  // spatial buckets: one feature row (8 image rows) x nxb column strips, so that the 4 x (strip + 3) cells the taps of
+  // consecutive keypoints touch (~20 KB at 16-cell strips) stay in L1 for all the CTAs resident on the SM
+  const int nxb = max(1, min(8, SAMPLE_MAX_ROWS / Hm));
+  const uint32_t xw = (uint32_t)((W + nxb - 1) / nxb);
+  auto bucket_of = [&](unsigned long long key) {
+    const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
+    const uint32_t yy = lin / (uint32_t)W, xx = lin - yy * (uint32_t)W;
+    return min((int)((yy >> 3) * (uint32_t)nxb + xx / xw), SAMPLE_MAX_ROWS - 1);
+  };
   for (int i = tid; i < SAMPLE_MAX_ROWS; i += SAMPLE_THREADS) sHist[i] = 0;
   __syncthreads();
   for (int r = tid; r < nv; r += SAMPLE_THREADS) {
     const unsigned long long key = sorted[(int64_t)b * cap + r];
     sKey[r] = key;
-    const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
-    atomicAdd(&sHist[min((int)(lin / (uint32_t)W) >> 3, SAMPLE_MAX_ROWS - 1)], 1);
+    atomicAdd(&sHist[bucket_of(key)], 1);
   }
   __syncthreads();
   if (tid < 32) {   // exclusive scan of the row histogram (<= 512 buckets) by one warp
@@ -610,8 +633,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 4) sample_desc_sorted_kernel(
   }
   __syncthreads();
   for (int r = tid; r < nv; r += SAMPLE_THREADS) {
-    const uint32_t lin = 0xffffffffu - (uint32_t)(sKey[r] & 0xffffffffu);
-    const int pos = atomicAdd(&sHist[min((int)(lin / (uint32_t)W) >> 3, SAMPLE_MAX_ROWS - 1)], 1);
+    const int pos = atomicAdd(&sHist[bucket_of(sKey[r])], 1);
     sOrder[pos] = (unsigned short)r;
   }
   __syncthreads();
@@ -648,8 +670,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 4) sample_desc_sorted_kernel(
     const unsigned long long key = sKey[valid ? r : 0];
     const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
     const int x = (int)(lin % (uint32_t)W), y = (int)(lin / (uint32_t)W);
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) o = bicubic4(fb, db, x, y, H, W, Hm, Wm, l16);
+    float4 o = bicubic4<true>(fb, db, x, y, H, W, Hm, Wm, l16);   // (an odd tail's idle half-warp samples slot 0 again and drops it)
+    if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
     float ss = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
 #pragma unroll
     for (int s = 8; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
