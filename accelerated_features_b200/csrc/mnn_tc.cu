@@ -841,7 +841,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     tc::tmem_relinquish_2sm();
   }
   tc::tc_fence_before();
-  __syncthreads();                 // (the cluster barrier below already orders this; compute-sanitizer racecheck only models the CTA one)
+  __syncthreads();                 // (the cluster barrier below already orders this)
   tc::cluster_sync();              // barrier inits + TMEM allocation of both CTAs visible before any remote signal
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;

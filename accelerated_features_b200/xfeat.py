@@ -675,8 +675,27 @@ class XFeat(torch.nn.Module):
 
     def _match_star_device(self, im_set1, im_set2, top_k: int, div255=False):
         da, db = (div255 if isinstance(div255, (list, tuple)) else (div255, div255))
-        o1 = self._dense_device(im_set1, top_k, True, da)
-        o2 = self._dense_device(im_set2, top_k, True, db)
+        if (isinstance(im_set2, torch.Tensor) and not im_set2.is_cuda and im_set2.dim() == 4
+                and isinstance(im_set1, torch.Tensor) and not im_set1.is_cuda):
+            # host inputs: the second set travels on the copy stream while the first set is being extracted
+            if self._pipe is None:
+                self._pipe = XFeat._Pipe(self.dev)
+            main, copy = torch.cuda.current_stream(self.dev), self._pipe.copy
+            x1 = im_set1.to(self.dev, non_blocking=True)
+            x2 = torch.empty_like(im_set2, device=self.dev)       # from the compute stream's pool (it is read there)
+            start, done = torch.cuda.Event(), torch.cuda.Event()
+            start.record(main)
+            with torch.cuda.stream(copy):
+                copy.wait_event(start)                            # (the block may still be in use by earlier kernels)
+                x2.copy_(im_set2, non_blocking=True)
+                done.record(copy)
+            o1 = self._dense_device(x1, top_k, True, da)
+            main.wait_event(done)
+            im_set1, im_set2 = x1, x2
+            o2 = self._dense_device(x2, top_k, True, db)
+        else:
+            o1 = self._dense_device(im_set1, top_k, True, da)
+            o2 = self._dense_device(im_set2, top_k, True, db)
         B, K0, _ = o1["descriptors"].shape
         K1 = o2["descriptors"].shape[1]
         if o2["descriptors"].shape[0] != B:
