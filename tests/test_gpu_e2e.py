@@ -133,6 +133,30 @@ def test_star_assets(xf, oracle_state, assets_vga, golden):
     assert isinstance(a0, np.ndarray) and a0.shape == a1.shape and a0.shape[1] == 2
 
 
+def test_constant_and_featureless_images(xf, oracle_state):
+    """Images without structure: all-zero and constant images give NO keypoints (InstanceNorm of a constant is 0), a horizontal
+    ramp a few dozen; the batch mixes them with a random image, and a pair with an empty side yields no matches (the reference's
+    single-pair `match` raises IndexError from torch.max there, xfeat.py:331-335; a batch must not abort)."""
+    g = torch.Generator().manual_seed(5)
+    ramp = torch.linspace(0, 1, 128).view(1, 1, 1, 128).expand(1, 3, 96, 128).contiguous()
+    x = torch.cat([torch.zeros(1, 3, 96, 128), torch.full((1, 3, 96, 128), 0.37), ramp, torch.randn(1, 3, 96, 128, generator=g)])
+    want, st = orc.detect_and_compute(oracle_state, x, 512, return_stages=True)
+    got = xf.detectAndCompute(x, top_k=512)
+    assert [len(w["keypoints"]) for w in want][:2] == [0, 0] and len(want[2]["keypoints"]) > 0
+    stats = _check_detect("featureless", got, want, st, 512)
+    assert [s["got"] for s in stats] == [s["want"] for s in stats]
+    for b in (0, 1):
+        assert got[b]["keypoints"].shape == (0, 2) and got[b]["descriptors"].shape == (0, 64) and got[b]["scores"].shape == (0,)
+    pairs = xf.match_xfeat_batch(x, x.flip(0), top_k=512)          # (zeros,randn) (const,ramp) (ramp,const) (randn,zeros)
+    assert all(a.shape == (0, 2) and b.shape == (0, 2) for a, b in pairs)
+    i0, i1 = xf.match(got[0]["descriptors"], got[3]["descriptors"])
+    assert i0.numel() == 0 and i1.numel() == 0
+    same = xf.match_xfeat_batch(x, x, top_k=512)                   # identical sets: a random image's keypoints match themselves
+    assert len(same[3][0]) == stats[3]["got"] and np.array_equal(same[3][0], same[3][1])
+    assert all(len(a) <= s["got"] for (a, _), s in zip(same, stats))   # (the ramp repeats descriptors down its columns: ties)
+    record("featureless_images", keypoints=[s["got"] for s in stats], differing=sum(s["differing"] for s in stats))
+
+
 def test_minimal_example_api(xf):
     """the reference's minimal_example.py sequence (shapes only; randn inputs)."""
     torch.manual_seed(0)
