@@ -591,10 +591,11 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 4) sample_desc_sorted_kernel(
     const unsigned long long* __restrict__ sorted, const int* __restrict__ n_keep, const float* __restrict__ feats,
     const float* __restrict__ den, int H, int W, int Hm, int Wm, int cap, int top_k, float rw, float rh, float* __restrict__ kpts,
     float* __restrict__ scores, float* __restrict__ desc, int* __restrict__ n_valid, int* __restrict__ kpts_int,
-    __half* __restrict__ desc_split, int split_rows) {
+    __half* __restrict__ desc_split, int split_rows, unsigned long long magic_w, unsigned long long magic_xw) {
   extern __shared__ unsigned char sm_raw[];
   unsigned long long* sKey = reinterpret_cast<unsigned long long*>(sm_raw);           // [top_k]
   unsigned short* sOrder = reinterpret_cast<unsigned short*>(sKey + top_k);            // [top_k]
+  unsigned short* sBkt = sOrder + top_k;                                               // [top_k] bucket of key r
   __shared__ int sHist[SAMPLE_MAX_ROWS];
   const int b = blockIdx.x, tid = threadIdx.x, part = blockIdx.y, nparts = gridDim.y;
   const int nk = n_keep[b];
@@ -604,17 +605,20 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 4) sample_desc_sorted_kernel(
   // consecutive keypoints touch (~20 KB at 16-cell strips) stay in L1 for all the CTAs resident on the SM
   const int nxb = max(1, min(8, SAMPLE_MAX_ROWS / Hm));
   const uint32_t xw = (uint32_t)((W + nxb - 1) / nxb);
+  // divisions by W and by the strip width through 2^40 reciprocals (exact for lin * d < 2^40; the host checks H*W*W)
   auto bucket_of = [&](unsigned long long key) {
     const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
-    const uint32_t yy = lin / (uint32_t)W, xx = lin - yy * (uint32_t)W;
-    return min((int)((yy >> 3) * (uint32_t)nxb + xx / xw), SAMPLE_MAX_ROWS - 1);
+    const uint32_t yy = (uint32_t)(((unsigned long long)lin * magic_w) >> 40), xx = lin - yy * (uint32_t)W;
+    return min((int)((yy >> 3) * (uint32_t)nxb + (uint32_t)(((unsigned long long)xx * magic_xw) >> 40)), SAMPLE_MAX_ROWS - 1);
   };
   for (int i = tid; i < SAMPLE_MAX_ROWS; i += SAMPLE_THREADS) sHist[i] = 0;
   __syncthreads();
   for (int r = tid; r < nv; r += SAMPLE_THREADS) {
     const unsigned long long key = sorted[(int64_t)b * cap + r];
     sKey[r] = key;
-    atomicAdd(&sHist[bucket_of(key)], 1);
+    const int bk = bucket_of(key);
+    sBkt[r] = (unsigned short)bk;
+    atomicAdd(&sHist[bk], 1);
   }
   __syncthreads();
   if (tid < 32) {   // exclusive scan of the row histogram (<= 512 buckets) by one warp
@@ -633,7 +637,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 4) sample_desc_sorted_kernel(
   }
   __syncthreads();
   for (int r = tid; r < nv; r += SAMPLE_THREADS) {
-    const int pos = atomicAdd(&sHist[bucket_of(sKey[r])], 1);
+    const int pos = atomicAdd(&sHist[sBkt[r]], 1);
     sOrder[pos] = (unsigned short)r;
   }
   __syncthreads();
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 4) sample_desc_sorted_kernel(
     const int r = valid ? (int)sOrder[i] : 0;
     const unsigned long long key = sKey[valid ? r : 0];
     const uint32_t lin = 0xffffffffu - (uint32_t)(key & 0xffffffffu);
-    const int x = (int)(lin % (uint32_t)W), y = (int)(lin / (uint32_t)W);
+    const int y = (int)(((unsigned long long)lin * magic_w) >> 40), x = (int)lin - y * W;
     float4 o = bicubic4<true>(fb, db, x, y, H, W, Hm, Wm, l16);   // (an odd tail's idle half-warp samples slot 0 again and drops it)
     if (!valid) o = make_float4(0.f, 0.f, 0.f, 0.f);
     float ss = o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
@@ -807,13 +811,16 @@ extern "C" int xfeat_detect_sparse_split(xfeat_ctx* ctx, const float* d_feats, c
   // one-CTA-per-image spatially ordered variant: L1-friendly, measured 268 vs 330 us at B = 128 x 4096 keypoints; it
   // needs enough images to fill the GPU (XFEAT_SAMPLE_GENERIC=1 forces the generic kernel)
   static const bool force_generic = getenv("XFEAT_SAMPLE_GENERIC") != nullptr;
-  if (!force_generic && B >= 32 && top_k <= xf::SAMPLE_MAX_K && Hm <= xf::SAMPLE_MAX_ROWS) {
-    const size_t smem = (size_t)top_k * (sizeof(unsigned long long) + sizeof(unsigned short));
+  if (!force_generic && B >= 32 && top_k <= xf::SAMPLE_MAX_K && Hm <= xf::SAMPLE_MAX_ROWS && (int64_t)H * W * W < (1ll << 40)) {
+    const size_t smem = (size_t)top_k * (sizeof(unsigned long long) + 2 * sizeof(unsigned short));
+    const int nxb = std::max(1, std::min(8, xf::SAMPLE_MAX_ROWS / Hm));
+    const unsigned xw = (unsigned)((W + nxb - 1) / nxb);
+    const unsigned long long magic_w = (1ull << 40) / (unsigned)W + 1, magic_xw = (1ull << 40) / xw + 1;
     XF_DYN_SMEM(xf::sample_desc_sorted_kernel, smem);
     const int parts = std::max(1, std::min(xf::SAMPLE_PARTS, top_k / 512));
     xf::sample_desc_sorted_kernel<<<dim3(B, parts), xf::SAMPLE_THREADS, smem, st>>>(ws.sorted, ws.n_keep, d_feats, ws.den, H, W, Hm, Wm, cap,
                                                                       top_k, rw, rh, d_kpts, d_scores, d_desc, d_n_valid,
-                                                                      d_kpts_int, (__half*)d_desc_split, split_rows);
+                                                                      d_kpts_int, (__half*)d_desc_split, split_rows, magic_w, magic_xw);
   } else {
     const int64_t slots = (int64_t)B * top_k;
     if (d_desc_split && split_rows > top_k)   // this kernel only visits the top_k slots: the matcher's padding rows are cleared here
