@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, Iterable, Iterator, List, Optional, Tuple
 
 import numpy as np
@@ -21,7 +22,7 @@ from . import _lib
 from . import weights as _weights
 
 _F32 = np.float32
-_D2H_ON_MAIN = bool(__import__("os").environ.get("XFEAT_STREAM_D2H_MAIN"))   # A/B switch of match_xfeat_stream (results on the compute stream)
+_D2H_ON_MAIN = bool(os.environ.get("XFEAT_STREAM_D2H_MAIN"))   # A/B switch of match_xfeat_stream: results leave on the compute stream
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
