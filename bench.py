@@ -93,7 +93,7 @@ class ClockSampler:
 # CPU arm: the unmodified reference (oracle/_ref), CUDA hidden.  Runs in its own process (CUDA_VISIBLE_DEVICES='' must be
 # exported before torch is imported: the reference picks CUDA when it sees a device, modules/xfeat.py:25).
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_arm(config: str, n_pairs: int, repeats: int, warmup: int, seed: int = 0):
+def cpu_arm(config: str, n_pairs: int, repeats: int, warmup: int, seed: int = 0, budget_s: float = 270.0):
     import torch
     assert not torch.cuda.is_available(), "the CPU arm must not see a GPU"
     cfg = CONFIGS[config]
@@ -131,7 +131,15 @@ def cpu_arm(config: str, n_pairs: int, repeats: int, warmup: int, seed: int = 0)
                 n += len(i0)
             return n
 
-    for _ in range(warmup):
+    # honour (warmup, repeats) as long as the whole run stays inside `budget_s`; the first step is timed to project it
+    t0 = time.perf_counter()
+    step()
+    t_first = time.perf_counter() - t0
+    fit = max(2, int(budget_s / max(t_first, 1e-3)))
+    if warmup + repeats > fit:
+        warmup = max(1, min(warmup, fit // 5))
+        repeats = max(1, fit - warmup)
+    for _ in range(max(0, warmup - 1)):                # (the timed first step was the first warm-up step)
         step()
     times = []
     for _ in range(repeats):
@@ -139,7 +147,7 @@ def cpu_arm(config: str, n_pairs: int, repeats: int, warmup: int, seed: int = 0)
         step()
         times.append(time.perf_counter() - t0)
     return {"pairs_per_s": n_pairs / statistics.median(times), "seconds": sum(times), "threads": torch.get_num_threads(),
-            "kind": kind, "n_pairs": n_pairs, "repeats": repeats, "torch": torch.__version__}
+            "kind": kind, "n_pairs": n_pairs, "repeats": repeats, "warmup": max(1, warmup), "torch": torch.__version__}
 
 
 def cpu_arm_subprocess(config: str, n_pairs: int, repeats: int, warmup: int):
@@ -168,12 +176,13 @@ def run_reference(args):
         return
     cfg = CONFIGS[args.config]
     n_pairs = cfg["cpu_pairs"]
-    steps = max(1, min(args.steps, 3))                 # B=64 VGA is ~5-10 s per step on the host: keep the run within minutes
-    c = cpu_arm_subprocess(args.config, n_pairs, steps, 1 if args.warmup > 0 else 0)
+    # a step = the full batch (B = 64 VGA pairs: ~10 s on the host, 25 steps ~ 4 min).  --steps / --warmup are honoured unless
+    # the projected run exceeds 270 s, in which case the worker shortens it and the line reports what was actually run.
+    c = cpu_arm_subprocess(args.config, n_pairs, max(1, args.steps), max(1, args.warmup))
     v = c["pairs_per_s"]
     line = {
-        "impl": "reference", "metric": cfg["metric"], "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1 if args.warmup > 0 else 0, "steps_requested": args.steps, "ms_per_step": 1e3 * n_pairs / v,
+        "impl": "reference", "metric": cfg["metric"], "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": c["repeats"],
+        "warmup": c["warmup"], "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": 1e3 * n_pairs / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic randn",
         "config": {"workload": cfg["workload"], "pairs_per_gpu": n_pairs, "top_k": TOPK,
                    "note": "CPU arm: one host, no GPU" + ("" if n_pairs == BATCH else f"; {n_pairs} pairs per step instead of {BATCH} (scaled)")},
