@@ -261,6 +261,169 @@ __global__ void __launch_bounds__(256) gray_identity_u8hwc_kernel(const unsigned
   }
 }
 
+// Gray conversion + InstanceNorm in ONE pass for images at network resolution that fit the shared memory of a thread-block
+// cluster (VGA: 1.2 MB of gray = 8 CTAs x 150 KB).  A cluster owns an image: every CTA converts its eighth into shared memory
+// and sums it (fp64), the eight partial sums are exchanged through distributed shared memory (read in rank order by every CTA:
+// the statistics are deterministic, unlike the atomics of the two-kernel form), and the normalised values are written from
+// shared memory.  The gray image is never written to / re-read from HBM: 16 B in + 4 B out per pixel instead of 16 + 4 + 4 + 4.
+// Per-pixel arithmetic is that of gray_identity_f32_kernel / gray_identity_u8hwc_kernel and instnorm_kernel.
+constexpr int GN_THREADS = 1024, GN_CLUSTER = 8;
+constexpr size_t GN_MAX_SMEM = 200 * 1024;
+
+__device__ __forceinline__ double ld_dsmem_f64(uint32_t cluster_addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(cluster_addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t gn_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void gn_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int MODE>   // 0: fp32 planes (C channels, unit pixel stride), 1: uint8 HWC (3 interleaved channels)
+__global__ void __cluster_dims__(GN_CLUSTER, 1, 1) __launch_bounds__(GN_THREADS, 1)
+    gray_norm_cluster_kernel(const void* __restrict__ img, int C, int64_t sb, int64_t sc, int64_t sh, int div255, int H, int W4,
+                             float* __restrict__ xn, double* __restrict__ stats) {
+  extern __shared__ float4 sG[];            // this CTA's share of the gray image, 4-pixel groups
+  __shared__ double sRed[2][GN_THREADS / 32];
+  __shared__ double sPart[2];               // this CTA's (sum, sum of squares): read by the whole cluster
+  __shared__ float sNorm[2];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const unsigned rank = gn_cluster_rank();
+  const unsigned per = (unsigned)H * (unsigned)W4 / GN_CLUSTER, e0 = rank * per;
+  double s = 0.0, ss = 0.0;
+  for (unsigned i0 = 0; i0 < per; i0 += 2 * GN_THREADS) {
+    float4 g[2];
+    bool in[2];
+    if (MODE == 0) {
+      const float* p[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const unsigned i = i0 + k * GN_THREADS + tid;
+        in[k] = i < per;
+        const unsigned e = in[k] ? e0 + i : e0;
+        const unsigned y = e / (unsigned)W4, x4 = e - y * (unsigned)W4;
+        p[k] = (const float*)img + (int64_t)b * sb + (int64_t)y * sh + 4 * x4;
+        g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int c0 = 0; c0 < C; c0 += 4) {
+        float4 l[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            l[u][k] = (c0 + u < C && in[k]) ? __ldg(reinterpret_cast<const float4*>(p[k] + (int64_t)(c0 + u) * sc))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c0 + u < C) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              float4 v = l[u][k];
+              if (div255) { v.x = __fdiv_rn(v.x, 255.f); v.y = __fdiv_rn(v.y, 255.f); v.z = __fdiv_rn(v.z, 255.f); v.w = __fdiv_rn(v.w, 255.f); }
+              g[k].x = __fadd_rn(g[k].x, v.x); g[k].y = __fadd_rn(g[k].y, v.y); g[k].z = __fadd_rn(g[k].z, v.z); g[k].w = __fadd_rn(g[k].w, v.w);
+            }
+          }
+        }
+      }
+      if (C != 1) {
+        const float fc = (float)C;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          g[k].x = __fdiv_rn(g[k].x, fc); g[k].y = __fdiv_rn(g[k].y, fc); g[k].z = __fdiv_rn(g[k].z, fc); g[k].w = __fdiv_rn(g[k].w, fc);
+        }
+      }
+    } else {
+      uint32_t w[2][3];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const unsigned i = i0 + k * GN_THREADS + tid;
+        in[k] = i < per;
+        const unsigned e = in[k] ? e0 + i : e0;
+        const unsigned y = e / (unsigned)W4, x4 = e - y * (unsigned)W4;
+        const uint32_t* p = reinterpret_cast<const uint32_t*>((const unsigned char*)img + (int64_t)b * sb + (int64_t)y * sh) + 3 * x4;
+        w[k][0] = __ldg(p); w[k][1] = __ldg(p + 1); w[k][2] = __ldg(p + 2);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint32_t w0 = w[k][0], w1 = w[k][1], w2 = w[k][2];
+        const unsigned char by[12] = {(unsigned char)(w0), (unsigned char)(w0 >> 8), (unsigned char)(w0 >> 16), (unsigned char)(w0 >> 24),
+                                      (unsigned char)(w1), (unsigned char)(w1 >> 8), (unsigned char)(w1 >> 16), (unsigned char)(w1 >> 24),
+                                      (unsigned char)(w2), (unsigned char)(w2 >> 8), (unsigned char)(w2 >> 16), (unsigned char)(w2 >> 24)};
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float v = (float)by[3 * i + c];
+            if (div255) v = __fdiv_rn(v, 255.f);
+            acc = __fadd_rn(acc, v);
+          }
+          o[i] = __fdiv_rn(acc, 3.f);
+        }
+        g[k] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (in[k]) {
+        sG[i0 + k * GN_THREADS + tid] = g[k];
+        s += ((double)g[k].x + (double)g[k].y) + ((double)g[k].z + (double)g[k].w);
+        ss += (double)g[k].x * g[k].x + (double)g[k].y * g[k].y + (double)g[k].z * g[k].z + (double)g[k].w * g[k].w;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+  if (lane == 0) { sRed[0][warp] = s; sRed[1][warp] = ss; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0, c2 = 0;
+    for (int i = 0; i < GN_THREADS / 32; ++i) { a += sRed[0][i]; c2 += sRed[1][i]; }
+    sPart[0] = a; sPart[1] = c2;
+  }
+  gn_cluster_sync();                                   // every CTA's partial sums are visible cluster-wide
+  if (tid == 0) {
+    const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(&sPart[0]), a1 = (uint32_t)__cvta_generic_to_shared(&sPart[1]);
+    double sum = 0, sq = 0;
+    for (unsigned r = 0; r < GN_CLUSTER; ++r) {         // rank order: the same value in every CTA, run to run
+      uint32_t ra, rb;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a0), "r"(r));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(a1), "r"(r));
+      sum += ld_dsmem_f64(ra);
+      sq += ld_dsmem_f64(rb);
+    }
+    const double n = (double)H * (double)W4 * 4.0;       // as instnorm_kernel
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    if (var < 0) var = 0;
+    sNorm[0] = (float)mean;
+    sNorm[1] = (float)(1.0 / sqrt(var + 1e-5));
+    if (rank == 0) { stats[2 * b] = sum; stats[2 * b + 1] = sq; }
+  }
+  __syncthreads();
+  const float meanf = sNorm[0], invstd = sNorm[1];
+  float4* out = reinterpret_cast<float4*>(xn) + (int64_t)b * H * W4 + e0;
+  for (unsigned i = tid; i < per; i += GN_THREADS) {
+    float4 v = sG[i];
+    v.x = __fmul_rn(__fsub_rn(v.x, meanf), invstd);
+    v.y = __fmul_rn(__fsub_rn(v.y, meanf), invstd);
+    v.z = __fmul_rn(__fsub_rn(v.z, meanf), invstd);
+    v.w = __fmul_rn(__fsub_rn(v.w, meanf), invstd);
+    out[i] = v;
+  }
+  gn_cluster_sync();                                   // no CTA leaves while its partial sums may still be read
+}
+
 // InstanceNorm2d(1): (g - mean) * rsqrt(var_biased + 1e-5), float4 vectorised, in place.
 __global__ void __launch_bounds__(256) instnorm_kernel(float* __restrict__ gray, const double* __restrict__ stats,
                                                        int HW4) {
@@ -345,6 +508,23 @@ extern "C" int xfeat_preprocess_scaled(const void* d_img, int dtype, int B, int 
                     stride_b % 4 == 0 && stride_c % 4 == 0 && stride_h % 4 == 0;
   const bool fast_u8 = dtype == XF_DTYPE_U8 && Hi == H && Wi == W && C == 3 && stride_c == 1 && stride_w == 3 &&
                        ((uintptr_t)d_img % 4) == 0 && stride_b % 4 == 0 && stride_h % 4 == 0;
+  // one-pass cluster form: the image's gray fits the shared memory of 8 CTAs (XFEAT_PREP_TWO_PASS=1 keeps the two-kernel form)
+  static const bool two_pass = getenv("XFEAT_PREP_TWO_PASS") != nullptr;
+  const size_t gn_smem = (size_t)H * W * sizeof(float) / xf::GN_CLUSTER;
+  if (!two_pass && (fast || fast_u8) && (H * (W / 4)) % xf::GN_CLUSTER == 0 && gn_smem <= xf::GN_MAX_SMEM) {
+    dim3 gc(xf::GN_CLUSTER, B);
+    if (fast_u8) {
+      XF_DYN_SMEM(xf::gray_norm_cluster_kernel<1>, gn_smem);
+      xf::gray_norm_cluster_kernel<1><<<gc, xf::GN_THREADS, gn_smem, st>>>(d_img, 3, stride_b, 1, stride_h, div255, H, W / 4, d_xn,
+                                                                          d_stats);
+    } else {
+      XF_DYN_SMEM(xf::gray_norm_cluster_kernel<0>, gn_smem);
+      xf::gray_norm_cluster_kernel<0><<<gc, xf::GN_THREADS, gn_smem, st>>>(d_img, C, stride_b, stride_c, stride_h, div255, H, W / 4,
+                                                                          d_xn, d_stats);
+    }
+    XF_LAUNCH_CHECK();
+    return XF_OK;
+  }
   if (fast_u8) {
     dim3 g4(xf::cdiv(W / 4, 64), xf::cdiv(H, 4), B);
     xf::gray_identity_u8hwc_kernel<<<g4, 256, 0, st>>>((const unsigned char*)d_img, stride_b, stride_h, div255, H, W / 4, d_xn,

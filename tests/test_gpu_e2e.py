@@ -157,6 +157,24 @@ def test_constant_and_featureless_images(xf, oracle_state):
     record("featureless_images", keypoints=[s["got"] for s in stats], differing=sum(s["differing"] for s in stats))
 
 
+def test_run_to_run_bitwise_reproducible(xf):
+    """The sparse VGA path has no order-dependent arithmetic (the image statistics are reduced in rank order by the cluster
+    kernel, candidate lists are sorted by unique keys, arg-max ties go to the lowest index): repeated runs give the same bits."""
+    g = torch.Generator().manual_seed(11)
+    x1 = torch.randn(8, 3, 480, 640, generator=g).cuda(); x2 = torch.randn(8, 3, 480, 640, generator=g).cuda()
+    runs = []
+    for _ in range(4):
+        mk0, mk1, cnt = xf._match_sparse_batch_device(x1, x2, 4096, -1)
+        c = cnt.tolist()
+        runs.append((c, [mk0[b, :c[b]].clone() for b in range(8)], [mk1[b, :c[b]].clone() for b in range(8)]))
+    for c, a0, a1 in runs[1:]:
+        assert c == runs[0][0]
+        assert all(torch.equal(u, v) for u, v in zip(a0, runs[0][1])) and all(torch.equal(u, v) for u, v in zip(a1, runs[0][2]))
+    o = [xf._detect_sparse_device(x1, 4096, 0.05) for _ in range(3)]
+    for k in ("keypoints", "scores", "descriptors", "n_valid"):
+        assert torch.equal(o[0][k], o[1][k]) and torch.equal(o[0][k], o[2][k]), k
+
+
 def test_minimal_example_api(xf):
     """the reference's minimal_example.py sequence (shapes only; randn inputs)."""
     torch.manual_seed(0)
