@@ -262,13 +262,14 @@ __global__ void __launch_bounds__(256) gray_identity_u8hwc_kernel(const unsigned
 }
 
 // Gray conversion + InstanceNorm in ONE pass for images at network resolution that fit the shared memory of a thread-block
-// cluster (VGA: 1.2 MB of gray = 8 CTAs x 150 KB).  A cluster owns an image: every CTA converts its eighth into shared memory
-// and sums it (fp64), the eight partial sums are exchanged through distributed shared memory (read in rank order by every CTA:
+// cluster (VGA: 1.2 MB of gray = 16 CTAs x 75 KB, two CTAs per SM so that clusters in different phases overlap).  A cluster owns an image: every CTA converts its share into shared memory
+// and sums it (fp64), the partial sums are exchanged through distributed shared memory (read in rank order by every CTA:
 // the statistics are deterministic, unlike the atomics of the two-kernel form), and the normalised values are written from
 // shared memory.  The gray image is never written to / re-read from HBM: 16 B in + 4 B out per pixel instead of 16 + 4 + 4 + 4.
-// Per-pixel arithmetic is that of gray_identity_f32_kernel / gray_identity_u8hwc_kernel and instnorm_kernel.
-constexpr int GN_THREADS = 1024, GN_CLUSTER = 8;
-constexpr size_t GN_MAX_SMEM = 200 * 1024;
+// Per-pixel arithmetic is that of gray_identity_f32_kernel and instnorm_kernel.  (The uint8 ingest keeps the two-kernel form:
+// measured through the streaming pipeline it is 3-4 % faster there, bench.py e2e_u8.)
+constexpr int GN_THREADS = 512;   // cluster of 16 (non-portable size, 2 CTAs per SM) when a sixteenth fits 100 KB, else 8
+constexpr size_t GN_MAX_SMEM = 200 * 1024, GN_SMEM_2PER_SM = 100 * 1024;
 
 __device__ __forceinline__ double ld_dsmem_f64(uint32_t cluster_addr) {
   double v;
@@ -284,45 +285,45 @@ __device__ __forceinline__ void gn_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int MODE>   // 0: fp32 planes (C channels, unit pixel stride), 1: uint8 HWC (3 interleaved channels)
-__global__ void __cluster_dims__(GN_CLUSTER, 1, 1) __launch_bounds__(GN_THREADS, 1)
-    gray_norm_cluster_kernel(const void* __restrict__ img, int C, int64_t sb, int64_t sc, int64_t sh, int div255, int H, int W4,
+__global__ void __launch_bounds__(GN_THREADS, 2)
+    gray_norm_cluster_kernel(const float* __restrict__ img, int C, int64_t sb, int64_t sc, int64_t sh, int div255, int H, int W4,
                              float* __restrict__ xn, double* __restrict__ stats) {
   extern __shared__ float4 sG[];            // this CTA's share of the gray image, 4-pixel groups
   __shared__ double sRed[2][GN_THREADS / 32];
   __shared__ double sPart[2];               // this CTA's (sum, sum of squares): read by the whole cluster
   __shared__ float sNorm[2];
   const int b = blockIdx.y, tid = threadIdx.x;
-  const unsigned rank = gn_cluster_rank();
-  const unsigned per = (unsigned)H * (unsigned)W4 / GN_CLUSTER, e0 = rank * per;
+  const unsigned rank = gn_cluster_rank(), nranks = gridDim.x;        // the cluster spans grid.x
+  const unsigned per = (unsigned)H * (unsigned)W4 / nranks, e0 = rank * per;
+  constexpr int U = 2;   // 4-pixel groups per thread and trip: 96 B of loads in flight per thread at 3 channels
   double s = 0.0, ss = 0.0;
-  for (unsigned i0 = 0; i0 < per; i0 += 2 * GN_THREADS) {
-    float4 g[2];
-    bool in[2];
-    if (MODE == 0) {
-      const float* p[2];
+  for (unsigned i0 = 0; i0 < per; i0 += U * GN_THREADS) {
+    float4 g[U];
+    bool in[U];
+    {
+      const float* p[U];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < U; ++k) {
         const unsigned i = i0 + k * GN_THREADS + tid;
         in[k] = i < per;
         const unsigned e = in[k] ? e0 + i : e0;
         const unsigned y = e / (unsigned)W4, x4 = e - y * (unsigned)W4;
-        p[k] = (const float*)img + (int64_t)b * sb + (int64_t)y * sh + 4 * x4;
+        p[k] = img + (int64_t)b * sb + (int64_t)y * sh + 4 * x4;
         g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       for (int c0 = 0; c0 < C; c0 += 4) {
-        float4 l[4][2];
+        float4 l[4][U];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
+          for (int k = 0; k < U; ++k)
             l[u][k] = (c0 + u < C && in[k]) ? __ldg(reinterpret_cast<const float4*>(p[k] + (int64_t)(c0 + u) * sc))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (c0 + u < C) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < U; ++k) {
               float4 v = l[u][k];
               if (div255) { v.x = __fdiv_rn(v.x, 255.f); v.y = __fdiv_rn(v.y, 255.f); v.z = __fdiv_rn(v.z, 255.f); v.w = __fdiv_rn(v.w, 255.f); }
               g[k].x = __fadd_rn(g[k].x, v.x); g[k].y = __fadd_rn(g[k].y, v.y); g[k].z = __fadd_rn(g[k].z, v.z); g[k].w = __fadd_rn(g[k].w, v.w);
@@ -333,44 +334,13 @@ __global__ void __cluster_dims__(GN_CLUSTER, 1, 1) __launch_bounds__(GN_THREADS,
       if (C != 1) {
         const float fc = (float)C;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < U; ++k) {
           g[k].x = __fdiv_rn(g[k].x, fc); g[k].y = __fdiv_rn(g[k].y, fc); g[k].z = __fdiv_rn(g[k].z, fc); g[k].w = __fdiv_rn(g[k].w, fc);
         }
       }
-    } else {
-      uint32_t w[2][3];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const unsigned i = i0 + k * GN_THREADS + tid;
-        in[k] = i < per;
-        const unsigned e = in[k] ? e0 + i : e0;
-        const unsigned y = e / (unsigned)W4, x4 = e - y * (unsigned)W4;
-        const uint32_t* p = reinterpret_cast<const uint32_t*>((const unsigned char*)img + (int64_t)b * sb + (int64_t)y * sh) + 3 * x4;
-        w[k][0] = __ldg(p); w[k][1] = __ldg(p + 1); w[k][2] = __ldg(p + 2);
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const uint32_t w0 = w[k][0], w1 = w[k][1], w2 = w[k][2];
-        const unsigned char by[12] = {(unsigned char)(w0), (unsigned char)(w0 >> 8), (unsigned char)(w0 >> 16), (unsigned char)(w0 >> 24),
-                                      (unsigned char)(w1), (unsigned char)(w1 >> 8), (unsigned char)(w1 >> 16), (unsigned char)(w1 >> 24),
-                                      (unsigned char)(w2), (unsigned char)(w2 >> 8), (unsigned char)(w2 >> 16), (unsigned char)(w2 >> 24)};
-        float o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float acc = 0.f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float v = (float)by[3 * i + c];
-            if (div255) v = __fdiv_rn(v, 255.f);
-            acc = __fadd_rn(acc, v);
-          }
-          o[i] = __fdiv_rn(acc, 3.f);
-        }
-        g[k] = make_float4(o[0], o[1], o[2], o[3]);
-      }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < U; ++k) {
       if (in[k]) {
         sG[i0 + k * GN_THREADS + tid] = g[k];
         s += ((double)g[k].x + (double)g[k].y) + ((double)g[k].z + (double)g[k].w);
@@ -395,7 +365,7 @@ __global__ void __cluster_dims__(GN_CLUSTER, 1, 1) __launch_bounds__(GN_THREADS,
   if (tid == 0) {
     const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(&sPart[0]), a1 = (uint32_t)__cvta_generic_to_shared(&sPart[1]);
     double sum = 0, sq = 0;
-    for (unsigned r = 0; r < GN_CLUSTER; ++r) {         // rank order: the same value in every CTA, run to run
+    for (unsigned r = 0; r < nranks; ++r) {             // rank order: the same value in every CTA, run to run
       uint32_t ra, rb;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a0), "r"(r));
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(a1), "r"(r));
@@ -508,20 +478,30 @@ extern "C" int xfeat_preprocess_scaled(const void* d_img, int dtype, int B, int 
                     stride_b % 4 == 0 && stride_c % 4 == 0 && stride_h % 4 == 0;
   const bool fast_u8 = dtype == XF_DTYPE_U8 && Hi == H && Wi == W && C == 3 && stride_c == 1 && stride_w == 3 &&
                        ((uintptr_t)d_img % 4) == 0 && stride_b % 4 == 0 && stride_h % 4 == 0;
-  // one-pass cluster form: the image's gray fits the shared memory of 8 CTAs (XFEAT_PREP_TWO_PASS=1 keeps the two-kernel form)
+  // one-pass cluster form: the image's gray fits the shared memory of a cluster (XFEAT_PREP_TWO_PASS=1 keeps the two-kernel form)
   static const bool two_pass = getenv("XFEAT_PREP_TWO_PASS") != nullptr;
-  const size_t gn_smem = (size_t)H * W * sizeof(float) / xf::GN_CLUSTER;
-  if (!two_pass && (fast || fast_u8) && (H * (W / 4)) % xf::GN_CLUSTER == 0 && gn_smem <= xf::GN_MAX_SMEM) {
-    dim3 gc(xf::GN_CLUSTER, B);
-    if (fast_u8) {
-      XF_DYN_SMEM(xf::gray_norm_cluster_kernel<1>, gn_smem);
-      xf::gray_norm_cluster_kernel<1><<<gc, xf::GN_THREADS, gn_smem, st>>>(d_img, 3, stride_b, 1, stride_h, div255, H, W / 4, d_xn,
-                                                                          d_stats);
-    } else {
-      XF_DYN_SMEM(xf::gray_norm_cluster_kernel<0>, gn_smem);
-      xf::gray_norm_cluster_kernel<0><<<gc, xf::GN_THREADS, gn_smem, st>>>(d_img, C, stride_b, stride_c, stride_h, div255, H, W / 4,
-                                                                          d_xn, d_stats);
-    }
+  const size_t img_bytes = (size_t)H * W * sizeof(float);
+  const int n4 = H * (W / 4);
+  int cl = 0;
+  if (n4 % 16 == 0 && img_bytes / 16 <= xf::GN_SMEM_2PER_SM) cl = 16;
+  else if (n4 % 8 == 0 && img_bytes / 8 <= xf::GN_MAX_SMEM) cl = 8;
+  if (!two_pass && fast && cl) {
+    const size_t gn_smem = img_bytes / cl;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cl, B);
+    cfg.blockDim = dim3(xf::GN_THREADS);
+    cfg.dynamicSmemBytes = gn_smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const int W4 = W / 4;
+    XF_DYN_SMEM(xf::gray_norm_cluster_kernel, gn_smem);
+    if (cl > 8) XF_CUDA(cudaFuncSetAttribute(xf::gray_norm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    XF_CUDA(cudaLaunchKernelEx(&cfg, xf::gray_norm_cluster_kernel, (const float*)d_img, C, stride_b, stride_c, stride_h, div255, H, W4,
+                               d_xn, d_stats));
     XF_LAUNCH_CHECK();
     return XF_OK;
   }
