@@ -485,7 +485,13 @@ extern "C" int xfeat_preprocess_scaled(const void* d_img, int dtype, int B, int 
   int cl = 0;
   if (n4 % 16 == 0 && img_bytes / 16 <= xf::GN_SMEM_2PER_SM) cl = 16;
   else if (n4 % 8 == 0 && img_bytes / 8 <= xf::GN_MAX_SMEM) cl = 8;
-  if (!two_pass && fast && cl) {
+  // largest cluster size this process has not seen refused (16 is a non-portable size); XFEAT_PREP_CLUSTER_MAX=8|0 starts lower
+  static int cluster_cap = getenv("XFEAT_PREP_CLUSTER_MAX") ? atoi(getenv("XFEAT_PREP_CLUSTER_MAX")) : 16;
+  while (!two_pass && fast && cl) {
+    if (cl > cluster_cap) {        // step down: 16 -> 8 -> two-kernel form
+      cl = (cl == 16 && cluster_cap >= 8 && n4 % 8 == 0 && img_bytes / 8 <= xf::GN_MAX_SMEM) ? 8 : 0;
+      continue;
+    }
     const size_t gn_smem = img_bytes / cl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cl, B);
@@ -499,11 +505,17 @@ extern "C" int xfeat_preprocess_scaled(const void* d_img, int dtype, int B, int 
     cfg.numAttrs = 1;
     const int W4 = W / 4;
     XF_DYN_SMEM(xf::gray_norm_cluster_kernel, gn_smem);
-    if (cl > 8) XF_CUDA(cudaFuncSetAttribute(xf::gray_norm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    XF_CUDA(cudaLaunchKernelEx(&cfg, xf::gray_norm_cluster_kernel, (const float*)d_img, C, stride_b, stride_c, stride_h, div255, H, W4,
-                               d_xn, d_stats));
-    XF_LAUNCH_CHECK();
-    return XF_OK;
+    cudaError_t e = cudaSuccess;
+    if (cl > 8) e = cudaFuncSetAttribute(xf::gray_norm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess)
+      e = cudaLaunchKernelEx(&cfg, xf::gray_norm_cluster_kernel, (const float*)d_img, C, stride_b, stride_c, stride_h, div255, H, W4,
+                             d_xn, d_stats);
+    if (e == cudaSuccess) {
+      XF_LAUNCH_CHECK();
+      return XF_OK;
+    }
+    (void)cudaGetLastError();      // a refused cluster shape is a launch-configuration error: nothing ran, try the next form
+    cluster_cap = cl == 16 ? 8 : 0;
   }
   if (fast_u8) {
     dim3 g4(xf::cdiv(W / 4, 64), xf::cdiv(H, 4), B);
