@@ -175,7 +175,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cfg = CONFIGS[args.config]
-    n_pairs = cfg["cpu_pairs"]
+    n_pairs = int(os.environ.get("XFEAT_BENCH_CPU_PAIRS", cfg["cpu_pairs"]))     # (tests shrink the batch; the line then says "scaled")
     # a step = the full batch (B = 64 VGA pairs: ~10 s on the host, 25 steps ~ 4 min).  --steps / --warmup are honoured unless
     # the projected run exceeds 270 s, in which case the worker shortens it and the line reports what was actually run.
     c = cpu_arm_subprocess(args.config, n_pairs, max(1, args.steps), max(1, args.warmup))
