@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(CT_THREADS2, 1) conv_tc_kernel(const __grid_co
               for (int k = 0; k < 4; ++k) tc::umma_f16(d, a1 + 2 * k, w0 + 2 * k, idesc, 1u);                    // lo.whi
             } else {
 #pragma unroll
-              for (int k = 0; k < C::KSTEPS; ++k) tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, idesc2, (tap | k) ? 1u : 0u);  // [hi|lo].[[whi|whi];[wlo|0]]
+              for (int k = 0; k < C::KSTEPS; ++k) {   // [hi|lo].[[whi|whi];[wlo|0]]; the lo K-steps of 128-byte rows skip the zero block
+                const bool lo_half = (C::ROWB == 128) && (k >= C::KSTEPS / 2);
+                tc::umma_f16(d, a0 + 2 * k, w0 + 2 * k, lo_half ? idesc : idesc2, (tap | k) ? 1u : 0u);
+              }
             }
           }
           tc::umma_commit(&a_empty[s]);

@@ -191,8 +191,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv_tc_halo_kernel(const __gri
             const uint64_t a0 = make_desc_rows_at<ROWB>(p_base + shift, P.desc_mode);
             const uint64_t wboth = tc::make_desc_rows<ROWB>(w_base + (uint32_t)(tap * 2) * C::W_GROUP);
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)   // [hi|lo] . [[whi|whi] ; [wlo|0]]  ->  cols [0,N): hi.whi + lo.whi, cols [N,2N): hi.wlo
-              tc::umma_f16(d, a0 + 2 * k, wboth + 2 * k, idesc2, (tap | k) ? 1u : 0u);
+            for (int k = 0; k < KSTEPS; ++k) {   // [hi|lo] . [[whi|whi] ; [wlo|0]]  ->  cols [0,N): hi.whi + lo.whi, cols [N,2N): hi.wlo
+              // 128-byte rows: K-steps 0,1 are the hi channels, 2,3 the lo channels, whose [wlo|0] rows multiply by zero -- those
+              // K-steps run at N = NOUT against the [whi|whi] rows only (a quarter less tensor work, 1 KB less operand traffic each)
+              const bool lo_half = (ROWB == 128) && (k >= KSTEPS / 2);
+              tc::umma_f16(d, a0 + 2 * k, wboth + 2 * k, lo_half ? idesc : idesc2, (tap | k) ? 1u : 0u);
+            }
           }
           tc::umma_commit(&p_empty[s]);
         }
