@@ -1,6 +1,8 @@
 // Image ingest: bilinear resize, channel mean, per-image instance normalisation.
 // Reference: preprocess_tensor (xfeat.py:219-240), XFeatModel.forward normalisation (model.py:135-136),
 // extract_dualscale's F.interpolate (xfeat.py:380-381).  All HBM-bound streaming kernels.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace xf {
@@ -486,7 +488,8 @@ extern "C" int xfeat_preprocess_scaled(const void* d_img, int dtype, int B, int 
   if (n4 % 16 == 0 && img_bytes / 16 <= xf::GN_SMEM_2PER_SM) cl = 16;
   else if (n4 % 8 == 0 && img_bytes / 8 <= xf::GN_MAX_SMEM) cl = 8;
   // largest cluster size this process has not seen refused (16 is a non-portable size); XFEAT_PREP_CLUSTER_MAX=8|0 starts lower
-  static int cluster_cap = getenv("XFEAT_PREP_CLUSTER_MAX") ? atoi(getenv("XFEAT_PREP_CLUSTER_MAX")) : 16;
+  static std::atomic<int> cluster_cap_a{getenv("XFEAT_PREP_CLUSTER_MAX") ? atoi(getenv("XFEAT_PREP_CLUSTER_MAX")) : 16};
+  int cluster_cap = cluster_cap_a.load(std::memory_order_relaxed);
   while (!two_pass && fast && cl) {
     if (cl > cluster_cap) {        // step down: 16 -> 8 -> two-kernel form
       cl = (cl == 16 && cluster_cap >= 8 && n4 % 8 == 0 && img_bytes / 8 <= xf::GN_MAX_SMEM) ? 8 : 0;
@@ -516,6 +519,7 @@ extern "C" int xfeat_preprocess_scaled(const void* d_img, int dtype, int B, int 
     }
     (void)cudaGetLastError();      // a refused cluster shape is a launch-configuration error: nothing ran, try the next form
     cluster_cap = cl == 16 ? 8 : 0;
+    cluster_cap_a.store(cluster_cap, std::memory_order_relaxed);
   }
   if (fast_u8) {
     dim3 g4(xf::cdiv(W / 4, 64), xf::cdiv(H, 4), B);
